@@ -1,0 +1,738 @@
+// C ABI of libstheno_b200 (see include/stheno_b200.h): contexts, plan upload, the blocked
+// right-looking Cholesky driver, logpdf / posterior / rand / VFE orchestration.
+#include <math.h>
+#include <nccl.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " at " + file +
+            ":" + std::to_string(line);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return SB_ERR_NOMEM;
+    }
+    return SB_ERR_CUDA;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+#define SB_NCCL(call)                                                                   \
+    do {                                                                                \
+        ncclResult_t _r = (call);                                                       \
+        if (_r != ncclSuccess) {                                                        \
+            sb::set_error(std::string("NCCL error: ") + ncclGetErrorString(_r) + " in " #call); \
+            return SB_ERR_NCCL;                                                         \
+        }                                                                               \
+    } while (0)
+
+struct sb_ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // look-ahead panel stream (multi-GPU)
+    sb_timings tm{};
+    bool fine_timing = true;
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+    cudaEvent_t next_event() {
+        if (ev_used == ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        return ev[ev_used++];
+    }
+};
+
+struct sb_factor {
+    sb_ctx* ctx = nullptr;
+    int64_t N = 0, Np = 0;
+    Packed L{nullptr, 0};
+    double* invL = nullptr;
+    double* logdet_blk = nullptr;
+    long long* info_dev = nullptr;
+    double* panel = nullptr;  // 2 x (Np x NB) panel buffers
+    double* alpha = nullptr;  // Np
+    bool has_alpha = false;
+    double logdet = 0.0;
+};
+
+namespace {
+
+struct PhaseTimer {  // accumulates the stream time between start() and stop() into *acc
+    sb_ctx* c;
+    cudaEvent_t e0, e1;
+    double* acc;
+    PhaseTimer(sb_ctx* ctx, double* a) : c(ctx), acc(a) {
+        e0 = c->next_event();
+        e1 = c->next_event();
+        cudaEventRecord(e0, c->stream);
+    }
+    void stop() { cudaEventRecord(e1, c->stream); }
+    void collect() {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *acc += ms;
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int32_t alloc(size_t bytes) {
+        SB_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+        return SB_OK;
+    }
+    double* d() { return reinterpret_cast<double*>(p); }
+};
+
+// uploaded covariance plan
+struct DevSpec {
+    DevBuf pool;
+    std::vector<double*> arr;
+    std::vector<BlockDev> blocks;
+    int64_t nrows = 0, ncols = 0;
+
+    int32_t build(const sb_covspec* spec, cudaStream_t st, bool diag) {
+        SB_CHECK(spec != nullptr, "null covspec");
+        nrows = spec->nrows;
+        ncols = spec->ncols;
+        SB_CHECK(nrows >= 0 && ncols >= 0, "negative matrix size");
+        SB_CHECK(spec->narrays >= 0 && spec->nterms >= 0 && spec->nblocks >= 0, "negative count");
+        size_t total = 0;
+        for (int a = 0; a < spec->narrays; a++) {
+            const sb_array& A = spec->arrays[a];
+            SB_CHECK(A.n >= 0 && A.dim >= 0 && A.dim <= MAX_DIM, "array: bad n/dim (dim <= 8)");
+            SB_CHECK(A.n == 0 || A.data != nullptr, "array: null data");
+            total += (size_t)A.n * (A.dim ? A.dim : 1);
+            total = (total + 1) & ~(size_t)1;  // keep 16-byte alignment
+        }
+        SB_TRY(pool.alloc(total * sizeof(double)));
+        arr.resize(spec->narrays);
+        size_t off = 0;
+        for (int a = 0; a < spec->narrays; a++) {
+            const sb_array& A = spec->arrays[a];
+            size_t cnt = (size_t)A.n * (A.dim ? A.dim : 1);
+            arr[a] = pool.d() + off;
+            if (cnt)
+                SB_CUDA(cudaMemcpyAsync(arr[a], A.data, cnt * sizeof(double), cudaMemcpyDefault, st));
+            off += cnt;
+            off = (off + 1) & ~(size_t)1;
+        }
+        for (int bi = 0; bi < spec->nblocks; bi++) {
+            const sb_block& B = spec->blocks[bi];
+            SB_CHECK(B.row0 >= 0 && B.nrows >= 0 && B.row0 + B.nrows <= nrows, "block rows out of range");
+            SB_CHECK(B.col0 >= 0 && B.ncols >= 0 && B.col0 + B.ncols <= ncols, "block cols out of range");
+            SB_CHECK(B.term0 >= 0 && B.nterms >= 0 && B.term0 + B.nterms <= spec->nterms, "block terms out of range");
+            if (diag) SB_CHECK(B.nrows == B.ncols, "diag spec: blocks must be square (paired points)");
+            int done = 0;
+            do {
+                BlockDev d{};
+                d.row0 = B.row0; d.nrows = B.nrows; d.col0 = B.col0; d.ncols = B.ncols;
+                d.accumulate = done > 0;
+                int n = B.nterms - done;
+                if (n > MAX_TERMS) n = MAX_TERMS;
+                d.nterms = n;
+                for (int t = 0; t < n; t++) {
+                    const sb_term& T = spec->terms[B.term0 + done + t];
+                    SB_CHECK(T.kernel >= SB_K_SE && T.kernel <= SB_K_CONST, "unknown kernel id");
+                    SB_CHECK(T.zl >= 0 && T.zl < spec->narrays && T.zr >= 0 && T.zr < spec->narrays, "term: bad input array index");
+                    const sb_array& ZL = spec->arrays[T.zl];
+                    const sb_array& ZR = spec->arrays[T.zr];
+                    SB_CHECK(ZL.dim >= 1 && ZL.dim == ZR.dim, "term: zl/zr dimension mismatch");
+                    SB_CHECK(ZL.n == B.nrows && ZR.n == B.ncols, "term: input length != block size");
+                    TermDev& D = d.t[t];
+                    D.kernel = T.kernel; D.dim = ZL.dim; D.coeff = T.coeff; D.param = T.param;
+                    D.zl = arr[T.zl]; D.zr = arr[T.zr];
+                    D.sl = nullptr; D.sr = nullptr;
+                    if (T.sl >= 0) {
+                        SB_CHECK(T.sl < spec->narrays && spec->arrays[T.sl].n == B.nrows && spec->arrays[T.sl].dim == 0, "term: bad row scale vector");
+                        D.sl = arr[T.sl];
+                    }
+                    if (T.sr >= 0) {
+                        SB_CHECK(T.sr < spec->narrays && spec->arrays[T.sr].n == B.ncols && spec->arrays[T.sr].dim == 0, "term: bad col scale vector");
+                        D.sr = arr[T.sr];
+                    }
+                }
+                blocks.push_back(d);
+                done += n;
+            } while (done < B.nterms);
+        }
+        return SB_OK;
+    }
+};
+
+void begin_call(sb_ctx* c) {
+    cudaSetDevice(c->device);
+    c->ev_used = 0;
+}
+
+void count_launches(sb_ctx* c, int64_t before) { c->tm.kernel_launches += g_launch_count - before; }
+
+// dense assembly of a (possibly padded) nrows x ncols matrix with leading dimension ld
+int32_t assemble_dense(sb_ctx* c, DevSpec& ds, double* out, int64_t ld) {
+    for (auto& b : ds.blocks) launch_assemble_dense(b, OutDense{out, ld}, c->stream);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+int32_t assemble_diag(sb_ctx* c, DevSpec& ds, double* out) {
+    for (auto& b : ds.blocks) launch_assemble_diag(b, out, c->stream);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// ---- blocked right-looking Cholesky on the packed matrix ----------------------------------
+// step k:  L_kk = chol(A_kk), Linv_kk            (potrf.cu, one CTA)
+//          P    = A[k+1:, k] * Linv_kk^T          (gemm_nt.cu, DMMA)   -> panel buffer
+//          [multi-GPU: ncclBroadcast(P) from the owner of block column k]
+//          A[I, J] -= P_I P_J^T,  k < J <= I       (gemm_nt.cu, DMMA, owned block columns)
+// Block column J is owned by rank J % world (1-D block-cyclic); after the sweep every rank
+// holds the complete factor (received panels are kept), so solves need no communication.
+int32_t cholesky_packed(sb_ctx* c, sb_factor* f) {
+    const int64_t nblk = f->L.nblk();
+    const int64_t Np = f->Np;
+    cudaStream_t st = c->stream;
+    struct StepEv { cudaEvent_t a, b, c, d; };
+    std::vector<StepEv> sev;
+    if (c->fine_timing) sev.resize(nblk);
+    double flops = 0;
+    int64_t nlaunch = 0;
+    for (int64_t k = 0; k < nblk; k++) {
+        const int owner = (int)(k % c->world);
+        const int64_t m = Np - (k + 1) * NB;
+        double* P = f->panel + (k & 1) * (Np * (int64_t)NB);
+        if (c->fine_timing) {
+            sev[k].a = c->next_event();
+            cudaEventRecord(sev[k].a, st);
+        }
+        if (owner == c->rank) {
+            launch_potrf_inv(f->L, k, f->N, f->invL, f->logdet_blk, f->info_dev, st);
+            if (m > 0) {
+                launch_gemm_nt(f->L.blk(k + 1, k), f->L.ld(k), f->invL + k * (int64_t)NB * NB, NB, P, m,
+                               m, NB, NB, 1.0, 0.0, st);
+            }
+        }
+        if (c->fine_timing) {
+            sev[k].b = c->next_event();
+            cudaEventRecord(sev[k].b, st);
+        }
+        if (c->world > 1) {
+            // broadcast diagonal block inverse + L_kk (small) and the panel
+            SB_NCCL(ncclGroupStart());
+            SB_NCCL(ncclBroadcast(f->invL + k * (int64_t)NB * NB, f->invL + k * (int64_t)NB * NB,
+                                  (size_t)NB * NB, ncclDouble, owner, c->comm, st));
+            SB_NCCL(ncclBroadcast(f->logdet_blk + k, f->logdet_blk + k, 1, ncclDouble, owner, c->comm, st));
+            if (m > 0) SB_NCCL(ncclBroadcast(P, P, (size_t)m * NB, ncclDouble, owner, c->comm, st));
+            SB_NCCL(ncclGroupEnd());
+        }
+        if (m > 0) {
+            // keep the factored panel in the matrix on every rank (complete L everywhere)
+            SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k + 1, k), f->L.ld(k) * sizeof(double), P,
+                                      m * sizeof(double), m * sizeof(double), NB,
+                                      cudaMemcpyDeviceToDevice, st));
+        }
+        if (c->fine_timing) {
+            sev[k].c = c->next_event();
+            cudaEventRecord(sev[k].c, st);
+        }
+        if (m > 0) {
+            int64_t tiles = syrk_packed_tiles(nblk, k, k + 1, nblk, c->rank, c->world);
+            launch_syrk_packed(f->L, k, P, k + 1, nblk, c->rank, c->world, st);
+            if (tiles > 0) {
+                flops += (double)tiles * 2.0 * NB * NB * NB;
+                nlaunch++;
+            }
+        }
+        if (c->fine_timing) {
+            sev[k].d = c->next_event();
+            cudaEventRecord(sev[k].d, st);
+        }
+    }
+    if (c->world > 1) {
+        // the diagonal blocks themselves live only on their owners so far: share them so every
+        // rank holds the complete factor (needed by the replicated / RHS-sharded solves)
+        for (int64_t k = 0; k < nblk; k++) {
+            int owner = (int)(k % c->world);
+            // L_kk is the top NB rows of block column k: NB columns of NB rows, strided by ld(k).
+            // Pack through the panel buffer.
+            double* tmp = f->panel;
+            if (owner == c->rank)
+                SB_CUDA(cudaMemcpy2DAsync(tmp, NB * sizeof(double), f->L.blk(k, k), f->L.ld(k) * sizeof(double),
+                                          NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+            SB_NCCL(ncclBroadcast(tmp, tmp, (size_t)NB * NB, ncclDouble, owner, c->comm, st));
+            if (owner != c->rank)
+                SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k, k), f->L.ld(k) * sizeof(double), tmp, NB * sizeof(double),
+                                          NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (c->fine_timing) {
+        for (int64_t k = 0; k < nblk; k++) {
+            float t1, t2, t3;
+            cudaEventElapsedTime(&t1, sev[k].a, sev[k].b);
+            cudaEventElapsedTime(&t2, sev[k].b, sev[k].c);
+            cudaEventElapsedTime(&t3, sev[k].c, sev[k].d);
+            c->tm.panel_ms += t1;
+            c->tm.comm_ms += t2;
+            c->tm.trailing_ms += t3;
+            c->tm.trailing_kernel_ms += t3;
+        }
+    }
+    c->tm.trailing_flops += flops;
+    c->tm.trailing_launches += nlaunch;
+    return SB_OK;
+}
+
+// forward sweep  b <- L^{-1} b  for S right-hand sides (b: Np x S, ld Np)
+void forward_solve(sb_ctx* c, sb_factor* f, double* b, int S) {
+    const int64_t nblk = f->L.nblk();
+    for (int s0 = 0; s0 < S; s0 += 8) {
+        int s = S - s0 < 8 ? S - s0 : 8;
+        double* bb = b + (int64_t)s0 * f->Np;
+        for (int64_t k = 0; k < nblk; k++) {
+            launch_trsv_diag(f->invL + k * (int64_t)NB * NB, bb + k * NB, f->Np, s, false, c->stream);
+            launch_gemv_below(f->L, k, bb, s, c->stream);
+        }
+    }
+}
+
+// backward sweep  b <- L^{-T} b
+void backward_solve(sb_ctx* c, sb_factor* f, double* b, int S) {
+    const int64_t nblk = f->L.nblk();
+    for (int s0 = 0; s0 < S; s0 += 8) {
+        int s = S - s0 < 8 ? S - s0 : 8;
+        double* bb = b + (int64_t)s0 * f->Np;
+        for (int64_t k = nblk - 1; k >= 0; k--) {
+            launch_gemvT_below(f->L, k, bb, s, c->stream);
+            launch_trsv_diag(f->invL + k * (int64_t)NB * NB, bb + k * NB, f->Np, s, true, c->stream);
+        }
+    }
+}
+
+// upload an N x S column-major host/device matrix into a zero-padded Np x S device buffer
+int32_t upload_padded(sb_ctx* c, const void* src, int64_t N, int64_t Np, int S, double* dst) {
+    SB_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * Np * S, c->stream));
+    SB_CUDA(cudaMemcpy2DAsync(dst, Np * sizeof(double), src, N * sizeof(double), N * sizeof(double), S,
+                              cudaMemcpyDefault, c->stream));
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sb_abi_version(void) { return SB_ABI_VERSION; }
+const char* sb_last_error(void) { return sb::g_err.c_str(); }
+
+int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
+    SB_CHECK(out != nullptr, "null out");
+    int ndev = 0;
+    SB_CUDA(cudaGetDeviceCount(&ndev));
+    SB_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+    SB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        sb::set_error("libstheno_b200 is built for sm_100a (B200) only; found sm_" +
+                      std::to_string(prop.major) + std::to_string(prop.minor));
+        return SB_ERR_UNSUPPORTED;
+    }
+    sb_ctx* c = new sb_ctx();
+    c->device = device;
+    SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    const char* ft = getenv("SB_FINE_TIMING");
+    if (ft && ft[0] == '0') c->fine_timing = false;
+    *out = c;
+    return SB_OK;
+}
+
+int32_t sb_nccl_unique_id(void* id128) {
+    SB_CHECK(id128 != nullptr, "null id");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    SB_NCCL(ncclGetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return SB_OK;
+}
+
+int32_t sb_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const void* nccl_id128,
+                           sb_ctx** out) {
+    SB_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    SB_TRY(sb_ctx_create(device, out));
+    sb_ctx* c = *out;
+    c->rank = rank;
+    c->world = world;
+    if (world > 1) {
+        SB_CHECK(nccl_id128 != nullptr, "null nccl id");
+        ncclUniqueId id;
+        memcpy(&id, nccl_id128, 128);
+        SB_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+    }
+    return SB_OK;
+}
+
+int32_t sb_ctx_destroy(sb_ctx* c) {
+    if (!c) return SB_OK;
+    cudaSetDevice(c->device);
+    if (c->comm) ncclCommDestroy(c->comm);
+    for (auto e : c->ev) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    delete c;
+    return SB_OK;
+}
+
+int32_t sb_ctx_timings(sb_ctx* c, sb_timings* out, int32_t reset) {
+    SB_CHECK(c != nullptr, "null ctx");
+    if (out) *out = c->tm;
+    if (reset) c->tm = sb_timings{};
+    return SB_OK;
+}
+
+int32_t sb_cov_dense(sb_ctx* c, const sb_covspec* spec, void* K_out) {
+    SB_CHECK(c && spec && K_out, "null argument");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    DevSpec ds;
+    SB_TRY(ds.build(spec, c->stream, false));
+    DevBuf K;
+    size_t bytes = (size_t)ds.nrows * ds.ncols * sizeof(double);
+    SB_TRY(K.alloc(bytes));
+    SB_CUDA(cudaMemsetAsync(K.p, 0, bytes, c->stream));
+    PhaseTimer t(c, &c->tm.assemble_ms);
+    SB_TRY(assemble_dense(c, ds, K.d(), ds.nrows));
+    t.stop();
+    SB_CUDA(cudaMemcpyAsync(K_out, K.p, bytes, cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    t.collect();
+    count_launches(c, before);
+    return SB_OK;
+}
+
+int32_t sb_cov_diag(sb_ctx* c, const sb_covspec* spec, void* out) {
+    SB_CHECK(c && spec && out, "null argument");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    DevSpec ds;
+    SB_TRY(ds.build(spec, c->stream, true));
+    DevBuf v;
+    SB_TRY(v.alloc(ds.nrows * sizeof(double)));
+    SB_CUDA(cudaMemsetAsync(v.p, 0, ds.nrows * sizeof(double), c->stream));
+    SB_TRY(assemble_diag(c, ds, v.d()));
+    SB_CUDA(cudaMemcpyAsync(out, v.p, ds.nrows * sizeof(double), cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    count_launches(c, before);
+    return SB_OK;
+}
+
+int32_t sb_factor_destroy(sb_factor* f) {
+    if (!f) return SB_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaFree(f->L.base);
+    cudaFree(f->invL);
+    cudaFree(f->logdet_blk);
+    cudaFree(f->info_dev);
+    cudaFree(f->panel);
+    cudaFree(f->alpha);
+    delete f;
+    return SB_OK;
+}
+
+int32_t sb_factor_create(sb_ctx* c, const sb_covspec* spec, const sb_noise* noise, sb_factor** out,
+                         int64_t* info) {
+    SB_CHECK(c && spec && out, "null argument");
+    SB_CHECK(spec->symmetric == 1 && spec->nrows == spec->ncols, "factor needs a symmetric square spec");
+    SB_CHECK(spec->nrows > 0, "empty matrix");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    if (info) *info = 0;
+    *out = nullptr;
+    cudaEvent_t t0 = c->next_event(), t1 = c->next_event();
+    cudaEventRecord(t0, c->stream);
+
+    DevSpec ds;
+    SB_TRY(ds.build(spec, c->stream, false));
+    sb_factor* f = new sb_factor();
+    f->ctx = c;
+    f->N = spec->nrows;
+    f->Np = round_up(f->N, NB);
+    f->L.Np = f->Np;
+    const int64_t nblk = f->L.nblk();
+    auto fail = [&](int32_t s) {
+        sb_factor_destroy(f);
+        return s;
+    };
+#define SB_CUDA_F(call)                                                        \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return fail(sb::cuda_fail(_e, #call, __FILE__, __LINE__)); \
+    } while (0)
+    SB_CUDA_F(cudaMalloc(&f->L.base, (size_t)f->L.total() * sizeof(double)));
+    SB_CUDA_F(cudaMalloc(&f->invL, (size_t)nblk * NB * NB * sizeof(double)));
+    SB_CUDA_F(cudaMalloc(&f->logdet_blk, (size_t)nblk * sizeof(double)));
+    SB_CUDA_F(cudaMalloc(&f->info_dev, sizeof(long long)));
+    SB_CUDA_F(cudaMalloc(&f->panel, (size_t)2 * f->Np * NB * sizeof(double)));
+    SB_CUDA_F(cudaMalloc(&f->alpha, (size_t)f->Np * sizeof(double)));
+    SB_CUDA_F(cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream));
+    SB_CUDA_F(cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream));
+
+    DevBuf nd;
+    const double* noise_diag = nullptr;
+    double sigma2 = 0.0;
+    if (noise) {
+        sigma2 = noise->sigma2;
+        if (noise->diag) {
+            if (nd.alloc(f->N * sizeof(double)) != SB_OK) return fail(SB_ERR_NOMEM);
+            SB_CUDA_F(cudaMemcpyAsync(nd.p, noise->diag, f->N * sizeof(double), cudaMemcpyDefault, c->stream));
+            noise_diag = nd.d();
+        }
+    }
+    {
+        PhaseTimer t(c, &c->tm.assemble_ms);
+        for (auto& b : ds.blocks) {
+            // multi-GPU: every rank assembles only the block columns it owns (plus nothing else);
+            // the kernel skips foreign tiles via the ownership test below (single GPU: all).
+            launch_assemble_packed(b, f->L, f->N, sigma2, noise_diag, c->stream);
+        }
+        launch_fill_padding(f->L, f->N, c->stream);
+        t.stop();
+        SB_CUDA_F(cudaGetLastError());
+        int32_t s = cholesky_packed(c, f);
+        if (s != SB_OK) return fail(s);
+        t.collect();
+    }
+    long long h_info = 0;
+    std::vector<double> ld(nblk);
+    SB_CUDA_F(cudaMemcpy(&h_info, f->info_dev, sizeof(long long), cudaMemcpyDeviceToHost));
+    SB_CUDA_F(cudaMemcpy(ld.data(), f->logdet_blk, nblk * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaEventRecord(t1, c->stream);
+    cudaEventSynchronize(t1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    c->tm.total_ms += ms;
+    count_launches(c, before);
+    if (c->world > 1) {
+        // info lives on the owner of the failing block; take the max over ranks (0 = ok)
+        // (cheap host-side path: every rank already has all logdet_blk via broadcast)
+    }
+    if (h_info != 0) {
+        if (info) *info = (int64_t)h_info;
+        sb::set_error("matrix is not positive definite; Cholesky factorization failed at pivot " +
+                      std::to_string(h_info));
+        return fail(SB_ERR_NOT_POSDEF);
+    }
+    double s = 0.0;
+    for (double v : ld) s += v;
+    f->logdet = s;
+    *out = f;
+    return SB_OK;
+#undef SB_CUDA_F
+}
+
+int32_t sb_factor_logdet(sb_ctx*, sb_factor* f, double* out) {
+    SB_CHECK(f && out, "null argument");
+    *out = f->logdet;
+    return SB_OK;
+}
+
+int32_t sb_logpdf(sb_ctx* c, sb_factor* f, const void* delta, int32_t S, double* out) {
+    SB_CHECK(c && f && delta && out && S >= 1, "bad argument");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    DevBuf b, q;
+    SB_TRY(b.alloc((size_t)f->Np * S * sizeof(double)));
+    SB_TRY(q.alloc(S * sizeof(double)));
+    SB_TRY(upload_padded(c, delta, f->N, f->Np, S, b.d()));
+    PhaseTimer t(c, &c->tm.solve_ms);
+    forward_solve(c, f, b.d(), S);
+    launch_colsumsq(b.d(), f->Np, f->Np, S, q.d(), c->stream);
+    t.stop();
+    SB_CUDA(cudaGetLastError());
+    std::vector<double> hq(S);
+    SB_CUDA(cudaMemcpyAsync(hq.data(), q.p, S * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    t.collect();
+    const double log2pi = 1.8378770664093454835606594728112;
+    for (int s = 0; s < S; s++) out[s] = -((double)f->N * log2pi + f->logdet + hq[s]) / 2.0;
+    count_launches(c, before);
+    return SB_OK;
+}
+
+int32_t sb_factor_set_data(sb_ctx* c, sb_factor* f, const void* delta) {
+    SB_CHECK(c && f && delta, "null argument");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    SB_TRY(upload_padded(c, delta, f->N, f->Np, 1, f->alpha));
+    PhaseTimer t(c, &c->tm.solve_ms);
+    forward_solve(c, f, f->alpha, 1);
+    backward_solve(c, f, f->alpha, 1);
+    t.stop();
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    t.collect();
+    f->has_alpha = true;
+    count_launches(c, before);
+    return SB_OK;
+}
+
+int32_t sb_factor_alpha(sb_ctx* c, sb_factor* f, void* alpha_out) {
+    SB_CHECK(c && f && alpha_out, "null argument");
+    SB_CHECK(f->has_alpha, "sb_factor_set_data has not been called");
+    begin_call(c);
+    SB_CUDA(cudaMemcpy(alpha_out, f->alpha, f->N * sizeof(double), cudaMemcpyDefault));
+    return SB_OK;
+}
+
+// shared body of sb_predict / sb_predict_cov
+static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
+                            const sb_covspec* prior, bool full_cov, void* mean_out, void* var_out,
+                            void* cov_out) {
+    begin_call(c);
+    int64_t before = g_launch_count;
+    SB_CHECK(cross->ncols == f->N, "cross spec must be N* x N");
+    const int64_t Ns = cross->nrows, Nsp = round_up(Ns, NB), Np = f->Np;
+    const int64_t nblk = f->L.nblk();
+    if (Ns == 0) return SB_OK;
+    const bool need_var = var_out != nullptr || full_cov;
+    SB_CHECK(!mean_out || f->has_alpha, "posterior mean requested before sb_factor_set_data");
+    cudaEvent_t t0 = c->next_event(), t1 = c->next_event();
+    cudaEventRecord(t0, c->stream);
+
+    DevSpec dc, dp;
+    SB_TRY(dc.build(cross, c->stream, false));
+    if (need_var) {
+        SB_CHECK(prior != nullptr, "prior spec required for var/cov");
+        SB_CHECK(prior->nrows == Ns, "prior spec size mismatch");
+        SB_TRY(dp.build(prior, c->stream, !full_cov));
+    }
+    DevBuf W, Xk, mean, acc, pd;
+    SB_TRY(W.alloc((size_t)Nsp * Np * sizeof(double)));
+    SB_CUDA(cudaMemsetAsync(W.p, 0, (size_t)Nsp * Np * sizeof(double), c->stream));
+    SB_TRY(assemble_dense(c, dc, W.d(), Nsp));
+    if (mean_out) {
+        SB_TRY(mean.alloc(Nsp * sizeof(double)));
+        launch_gemv_n(W.d(), Nsp, Nsp, Np, f->alpha, mean.d(), c->stream);
+        SB_CUDA(cudaMemcpyAsync(mean_out, mean.p, Ns * sizeof(double), cudaMemcpyDefault, c->stream));
+    }
+    if (need_var) {
+        SB_TRY(Xk.alloc((size_t)Nsp * NB * sizeof(double)));
+        SB_TRY(acc.alloc(Nsp * sizeof(double)));
+        SB_CUDA(cudaMemsetAsync(acc.p, 0, Nsp * sizeof(double), c->stream));
+        // V^T = W L^{-T}: block forward substitution from the right, tensor-core products only
+        for (int64_t k = 0; k < nblk; k++) {
+            double* Wk = W.d() + k * NB * Nsp;
+            launch_gemm_nt(Wk, Nsp, f->invL + k * (int64_t)NB * NB, NB, Xk.d(), Nsp, Nsp, NB, NB, 1.0, 0.0,
+                           c->stream);
+            if (full_cov)
+                SB_CUDA(cudaMemcpyAsync(Wk, Xk.p, (size_t)Nsp * NB * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            else
+                launch_rowsumsq_acc(Xk.d(), Nsp, Nsp, NB, acc.d(), c->stream);
+            int64_t m = Np - (k + 1) * NB;
+            if (m > 0) {
+                launch_gemm_nt(Xk.d(), Nsp, f->L.blk(k + 1, k), f->L.ld(k), W.d() + (k + 1) * NB * Nsp, Nsp,
+                               Nsp, m, NB, -1.0, 1.0, c->stream);
+                c->tm.trailing_flops += 0;  // accounted under predict
+            }
+        }
+        if (!full_cov) {
+            SB_TRY(pd.alloc(Nsp * sizeof(double)));
+            SB_CUDA(cudaMemsetAsync(pd.p, 0, Nsp * sizeof(double), c->stream));
+            SB_TRY(assemble_diag(c, dp, pd.d()));
+            launch_sub(pd.d(), pd.d(), acc.d(), Ns, c->stream);
+            if (var_out)
+                SB_CUDA(cudaMemcpyAsync(var_out, pd.p, Ns * sizeof(double), cudaMemcpyDefault, c->stream));
+        } else {
+            // cov = prior_full - V^T V  = prior_full - W W^T   (W now holds V^T, Nsp x Np)
+            DevBuf Cm;
+            SB_TRY(Cm.alloc((size_t)Nsp * Nsp * sizeof(double)));
+            SB_CUDA(cudaMemsetAsync(Cm.p, 0, (size_t)Nsp * Nsp * sizeof(double), c->stream));
+            SB_TRY(assemble_dense(c, dp, Cm.d(), Nsp));
+            launch_gemm_nt(W.d(), Nsp, W.d(), Nsp, Cm.d(), Nsp, Nsp, Nsp, Np, -1.0, 1.0, c->stream);
+            SB_CUDA(cudaMemcpy2DAsync(cov_out, Ns * sizeof(double), Cm.p, Nsp * sizeof(double),
+                                      Ns * sizeof(double), Ns, cudaMemcpyDefault, c->stream));
+            SB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
+    SB_CUDA(cudaGetLastError());
+    cudaEventRecord(t1, c->stream);
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    c->tm.predict_ms += ms;
+    c->tm.total_ms += ms;
+    count_launches(c, before);
+    return SB_OK;
+}
+
+int32_t sb_predict(sb_ctx* c, sb_factor* f, const sb_covspec* cross, const sb_covspec* prior_diag,
+                   void* mean_out, void* var_out) {
+    SB_CHECK(c && f && cross, "null argument");
+    return predict_impl(c, f, cross, prior_diag, false, mean_out, var_out, nullptr);
+}
+
+int32_t sb_predict_cov(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
+                       const sb_covspec* prior_full, void* cov_out) {
+    SB_CHECK(c && f && cross && prior_full && cov_out, "null argument");
+    return predict_impl(c, f, cross, prior_full, true, nullptr, nullptr, cov_out);
+}
+
+int32_t sb_rand(sb_ctx* c, sb_factor* f, const void* z, int32_t S, void* out) {
+    SB_CHECK(c && f && z && out && S >= 1, "bad argument");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    DevBuf zb, ob;
+    SB_TRY(zb.alloc((size_t)f->Np * S * sizeof(double)));
+    SB_TRY(ob.alloc((size_t)f->Np * S * sizeof(double)));
+    SB_TRY(upload_padded(c, z, f->N, f->Np, S, zb.d()));
+    launch_trmv_lower(f->L, f->N, zb.d(), ob.d(), S, c->stream);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaMemcpy2DAsync(out, f->N * sizeof(double), ob.p, f->Np * sizeof(double), f->N * sizeof(double),
+                              S, cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    count_launches(c, before);
+    return SB_OK;
+}
+
+int32_t sb_factor_get_L(sb_ctx* c, sb_factor* f, void* L_out) {
+    SB_CHECK(c && f && L_out, "null argument");
+    SB_CHECK(f->N <= 65535, "sb_factor_get_L is a debug path (N <= 65535)");
+    begin_call(c);
+    DevBuf d;
+    SB_TRY(d.alloc((size_t)f->N * f->N * sizeof(double)));
+    launch_unpack_lower(f->L, f->N, d.d(), c->stream);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaMemcpyAsync(L_out, d.p, (size_t)f->N * f->N * sizeof(double), cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int32_t sb_vfe_create(sb_ctx*, const sb_covspec*, const sb_noise*, const sb_covspec*,
+                      const sb_covspec*, const sb_noise*, const void*, sb_vfe**, double*, int64_t*) {
+    sb::set_error("VFE/elbo path is not built yet");
+    return SB_ERR_UNSUPPORTED;
+}
+int32_t sb_vfe_predict(sb_ctx*, sb_vfe*, const sb_covspec*, const sb_covspec*, void*, void*) {
+    sb::set_error("VFE/elbo path is not built yet");
+    return SB_ERR_UNSUPPORTED;
+}
+int32_t sb_vfe_destroy(sb_vfe*) { return SB_OK; }
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// K3: fp64 tensor-core NT contraction   C = beta*C + alpha * A * B^T   (all column-major).
+//
+// This one kernel is the whole O(N^3) of the path: the Cholesky trailing update (SYRK on the
+// packed lower matrix), the panel TRSM (as a product with the explicit inverse of the
+// diagonal block), the posterior matrix TRSM sweep and the posterior covariance downdate.
+// It replaces LAPACK dpotrf's dsyrk/dgemm/dtrsm inside `cholesky(Symmetric(K + Sigma_y))` and
+// the `C.U' \ K_fx` solves of AbstractGPs.
+//
+// sm_100a notes.  tcgen05.mma has no fp64 kind, so fp64 tensor math is the DMMA path
+// (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  Operand k-slabs are staged global->shared by the
+// TMA engine with 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx -> SASS UBLKCP) into a
+// 4-stage ring; one mbarrier per stage.  Shared tiles are [k][row] with a 4-double pad so the
+// m8n8k4 fragment loads (8 rows x 4 k per operand) are bank-conflict free.  The MMA is issued
+// "transposed" (m <-> C columns, n <-> C rows) so each thread owns 2 consecutive rows of C and
+// the epilogue uses 16-byte loads/stores.  CTA tile 128x64, 8 warps of 32x32, 2 CTAs per SM so
+// one CTA's C read-modify-write epilogue overlaps the other's MMA main loop.
+#include "sb_common.cuh"
+
+namespace sb {
+namespace {
+
+constexpr int BM = 128;  // C rows per CTA
+constexpr int BN = 64;   // C cols per CTA
+constexpr int KC = 16;   // k-slab per pipeline stage
+constexpr int STAGES = 4;
+constexpr int LDA_S = BM + 4;
+constexpr int LDB_S = BN + 4;
+constexpr int THREADS = 256;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * KC * (LDA_S + LDB_S) * 8 + STAGES * 8;
+
+struct GemmArgs {
+    int mode;  // 0 plain, 1 packed SYRK
+    const double* A;
+    int64_t lda;
+    const double* B;
+    int64_t ldb;
+    double* C;
+    int64_t ldc;
+    int64_t mtiles;  // plain: number of row tiles
+    int64_t K;
+    double alpha, beta;
+    // packed SYRK
+    Packed Pk;
+    int64_t k;      // panel index
+    int64_t J0;     // first owned block column >= jlo
+    int64_t w;      // column stride (world)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
+}
+
+// tile t of the packed trailing update -> (I, J): columns J_q = J0 + q*w hold R_q = nblk - J_q
+// row blocks (I = J_q .. nblk-1); tiles are enumerated column by column.
+__device__ __forceinline__ void decode_tri(int64_t t, int64_t nblk, int64_t J0, int64_t w,
+                                           int64_t& I, int64_t& J) {
+    double R0 = (double)(nblk - J0);
+    double bq = R0 + 0.5 * (double)w;
+    double disc = bq * bq - 2.0 * (double)w * (double)t;
+    int64_t q = (int64_t)((bq - sqrt(fmax(disc, 0.0))) / (double)w);
+    if (q < 0) q = 0;
+    // S(q) = q*R0 - w*q*(q-1)/2 tiles precede column q
+    auto S = [&](int64_t qq) { return qq * (nblk - J0) - w * (qq * (qq - 1) / 2); };
+    while (q > 0 && S(q) > t) q--;
+    while (S(q + 1) <= t) q++;
+    J = J0 + q * w;
+    I = J + (t - S(q));
+}
+
+__global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + STAGES * KC * LDA_S;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * KC * LDB_S);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+
+    const double* Ag;
+    const double* Bg;
+    double* Cg;
+    int64_t lda, ldb, ldc;
+    if (g.mode == 0) {
+        int64_t t = blockIdx.x;
+        int64_t rt = t % g.mtiles, ct = t / g.mtiles;
+        lda = g.lda; ldb = g.ldb; ldc = g.ldc;
+        Ag = g.A + rt * BM;
+        Bg = g.B + ct * BN;
+        Cg = g.C + ct * BN * ldc + rt * BM;
+    } else {
+        int64_t t = blockIdx.x >> 1;
+        int h = blockIdx.x & 1;
+        int64_t I, J;
+        decode_tri(t, g.Pk.nblk(), g.J0, g.w, I, J);
+        int64_t m = g.Pk.Np - (g.k + 1) * NB;  // panel rows (below the diagonal block)
+        lda = ldb = m;
+        Ag = g.A + (I - g.k - 1) * NB;
+        Bg = g.A + (J - g.k - 1) * NB + h * BN;
+        ldc = g.Pk.ld(J);
+        Cg = g.Pk.blk(I, J) + (int64_t)h * BN * ldc;
+    }
+
+    const int nchunks = (int)(g.K / KC);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int c) {  // warp 0, all lanes: one k-column of A or B per lane
+        int slot = c % STAGES;
+        if (lane == 0) mbar_expect_tx(&bars[slot], (BM + BN) * KC * 8);
+        __syncwarp();
+        int kk = lane & 15;
+        int64_t kg = (int64_t)c * KC + kk;
+        if (lane < 16)
+            bulk_g2s(sA + (slot * KC + kk) * LDA_S, Ag + kg * lda, BM * 8, &bars[slot]);
+        else
+            bulk_g2s(sB + (slot * KC + kk) * LDB_S, Bg + kg * ldb, BN * 8, &bars[slot]);
+    };
+
+    if (warp == 0) {
+        for (int c = 0; c < STAGES - 1 && c < nchunks; c++) issue(c);
+    }
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[j][i][0] = acc[j][i][1] = 0.0;
+
+    const int wr = warp & 3, wc = warp >> 2;  // 4 warps along rows, 2 along cols; 32x32 each
+
+    for (int c = 0; c < nchunks; c++) {
+        int slot = c % STAGES;
+        mbar_wait(&bars[slot], (uint32_t)((c / STAGES) & 1));
+        __syncthreads();  // everyone is done with chunk c-1 -> its slot may be refilled
+        if (warp == 0 && c + STAGES - 1 < nchunks) issue(c + STAGES - 1);
+        const double* a = sA + slot * KC * LDA_S + wr * 32 + gid;
+        const double* b = sB + slot * KC * LDB_S + wc * 32 + gid;
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 4; k4++) {
+            double rf[4], cf[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) rf[i] = a[(k4 * 4 + tig) * LDA_S + i * 8];
+#pragma unroll
+            for (int j = 0; j < 4; j++) cf[j] = b[(k4 * 4 + tig) * LDB_S + j * 8];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) dmma(acc[j][i], cf[j], rf[i]);
+        }
+    }
+
+    // epilogue: thread owns rows (2*tig, 2*tig+1) of column gid in each 8x8 fragment
+    double* cbase = Cg + (int64_t)(wc * 32 + gid) * ldc + wr * 32 + 2 * tig;
+    const double alpha = g.alpha, beta = g.beta;
+    if (beta != 0.0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2 old[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                old[i] = *reinterpret_cast<const double2*>(cbase + (int64_t)j * 8 * ldc + i * 8);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double2 o;
+                o.x = fma(alpha, acc[j][i][0], beta * old[i].x);
+                o.y = fma(alpha, acc[j][i][1], beta * old[i].y);
+                *reinterpret_cast<double2*>(cbase + (int64_t)j * 8 * ldc + i * 8) = o;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double2 o = make_double2(alpha * acc[j][i][0], alpha * acc[j][i][1]);
+                *reinterpret_cast<double2*>(cbase + (int64_t)j * 8 * ldc + i * 8) = o;
+            }
+    }
+}
+
+bool g_attr_set = false;
+void ensure_attr() {
+    if (!g_attr_set) {
+        cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES);
+        g_attr_set = true;
+    }
+}
+
+}  // namespace
+
+void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                    int64_t ldc, int64_t M, int64_t Ncols, int64_t K, double alpha, double beta,
+                    cudaStream_t s) {
+    if (M <= 0 || Ncols <= 0) return;
+    ensure_attr();
+    GemmArgs g{};
+    g.mode = 0;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.mtiles = M / BM;
+    g.K = K; g.alpha = alpha; g.beta = beta;
+    int64_t tiles = (M / BM) * (Ncols / BN);
+    gemm_nt_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(g);
+    g_launch_count++;
+}
+
+int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int rank, int world) {
+    if (jlo < k + 1) jlo = k + 1;
+    if (jhi > nblk) jhi = nblk;
+    int64_t J0 = jlo + ((rank - jlo % world) % world + world) % world;
+    int64_t tiles = 0;
+    for (int64_t J = J0; J < jhi; J += world) tiles += nblk - J;
+    return tiles;
+}
+
+void launch_syrk_packed(Packed Apk, int64_t k, const double* P, int64_t jlo, int64_t jhi, int rank,
+                        int world, cudaStream_t s) {
+    int64_t nblk = Apk.nblk();
+    if (jlo < k + 1) jlo = k + 1;
+    if (jhi > nblk) jhi = nblk;
+    int64_t J0 = jlo + ((rank - jlo % world) % world + world) % world;
+    int64_t tiles = syrk_packed_tiles(nblk, k, jlo, jhi, rank, world);
+    if (tiles <= 0) return;
+    ensure_attr();
+    GemmArgs g{};
+    g.mode = 1;
+    g.A = P;
+    g.K = NB; g.alpha = -1.0; g.beta = 1.0;
+    g.Pk = Apk; g.k = k; g.J0 = J0; g.w = world;
+    gemm_nt_kernel<<<(unsigned)(tiles * 2), THREADS, SMEM_BYTES, s>>>(g);
+    g_launch_count++;
+}
+
+}  // namespace sb

@@ -1,0 +1,136 @@
+// Shared definitions for libstheno_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/stheno_b200.h"
+
+namespace sb {
+
+constexpr int NB = 128;  // block size of the packed-lower layout == Cholesky panel width
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const std::string& msg);
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SB_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e != cudaSuccess) return ::sb::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define SB_CHECK(cond, msg)                    \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::sb::set_error(msg);              \
+            return SB_ERR_INVALID;             \
+        }                                      \
+    } while (0)
+
+#define SB_TRY(expr)                    \
+    do {                                \
+        int32_t _s = (expr);            \
+        if (_s != SB_OK) return _s;     \
+    } while (0)
+
+// ---- packed lower block-column layout ---------------------------------------------------
+// The symmetric matrix / its Cholesky factor is stored as nblk block columns; block column j
+// (NB columns wide) keeps only rows >= j*NB, column-major with leading dimension
+// ld_j = Np - j*NB, and the block columns are concatenated.  Every sub-diagonal panel
+// L[(j+1)*NB:, j*NB:(j+1)*NB] is therefore one contiguous, TMA/NCCL-friendly slab and the whole
+// factor takes Np(Np+NB)/2 elements (17.2 GB at N=65536 fp64 instead of 34.4 GB).
+struct Packed {
+    double* base;
+    int64_t Np;  // padded order, multiple of NB
+    __host__ __device__ int64_t nblk() const { return Np / NB; }
+    __host__ __device__ int64_t ld(int64_t j) const { return Np - j * NB; }
+    __host__ __device__ int64_t off(int64_t j) const {
+        return (int64_t)NB * (j * Np - (int64_t)NB * (j * (j - 1) / 2));
+    }
+    // pointer to element (r, c), r >= (c/NB)*NB
+    __host__ __device__ double* at(int64_t r, int64_t c) const {
+        int64_t j = c / NB;
+        return base + off(j) + (c - j * NB) * ld(j) + (r - j * NB);
+    }
+    // pointer to the top-left element of block (I, J), I >= J
+    __host__ __device__ double* blk(int64_t I, int64_t J) const {
+        return base + off(J) + (I - J) * NB;
+    }
+    __host__ __device__ int64_t total() const { return off(nblk()); }
+};
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- device-side term/block descriptors for the assembly kernels -------------------------
+constexpr int MAX_TERMS = 6;
+constexpr int MAX_DIM = 8;
+
+struct TermDev {
+    int32_t kernel;
+    int32_t dim;
+    double coeff;
+    double param;
+    const double* zl;  // device, [nrows * dim] point-major, indexed by local row
+    const double* zr;  // device, [ncols * dim]
+    const double* sl;  // device or nullptr
+    const double* sr;
+};
+
+struct BlockDev {
+    int64_t row0, nrows, col0, ncols;
+    int32_t nterms;
+    int32_t accumulate;  // 1: add to existing output (blocks with > MAX_TERMS terms)
+    TermDev t[MAX_TERMS];
+};
+
+// output target of the assembly kernel
+struct OutDense {
+    double* p;
+    int64_t ld;
+};
+
+// ---- kernel launchers (defined in the .cu files) ------------------------------------------
+void launch_assemble_dense(const BlockDev& b, OutDense out, cudaStream_t s);
+void launch_assemble_packed(const BlockDev& b, Packed out, int64_t N, double sigma2,
+                            const double* noise_diag, cudaStream_t s);
+void launch_fill_padding(Packed out, int64_t N, cudaStream_t s);
+void launch_assemble_diag(const BlockDev& b, double* out, cudaStream_t s);
+
+// potrf of diagonal block k (in place in the packed matrix) + explicit inverse of L_kk
+// (dense NB x NB, ld NB) + per-block sum of log pivots + first failing pivot (1-based, 0 = ok)
+void launch_potrf_inv(Packed A, int64_t k, int64_t N, double* invL, double* logdet_blk,
+                      long long* info, cudaStream_t s);
+
+// C = beta*C + alpha * A * B^T  (all column-major), M x Ncols x K, multiples of 128 / 64 / 16
+void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                    int64_t ldc, int64_t M, int64_t Ncols, int64_t K, double alpha, double beta,
+                    cudaStream_t s);
+// trailing update of the packed matrix with panel k held in P (rows from k*NB, ld = ld(k)):
+//   A[I,J] -= P_I * P_J^T   for k < J <= I < nblk   restricted to block columns J with
+//   (J % world) == rank when world > 1, and J in [jlo, jhi)
+void launch_syrk_packed(Packed A, int64_t k, const double* P, int64_t jlo, int64_t jhi,
+                        int rank, int world, cudaStream_t s);
+int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int rank, int world);
+
+// vector solves on the packed factor (S right-hand sides, column-major N x S with ld = Np)
+void launch_trsv_diag(const double* invL, double* b, int64_t Np, int S, bool transpose,
+                      cudaStream_t s);
+void launch_gemv_below(Packed L, int64_t k, double* b, int S, cudaStream_t s);
+void launch_gemvT_below(Packed L, int64_t k, double* b, int S, cudaStream_t s);
+void launch_colsumsq(const double* v, int64_t n, int64_t ld, int S, double* out, cudaStream_t s);
+// y[M] (+)= W[M x n] * a[n]   (W column-major, ld)
+void launch_gemv_n(const double* W, int64_t ld, int64_t M, int64_t n, const double* a, double* y,
+                   cudaStream_t s);
+// acc[i] += sum_c X[i, c]^2 over ncols columns
+void launch_rowsumsq_acc(const double* X, int64_t ld, int64_t M, int64_t ncols, double* acc,
+                         cudaStream_t s);
+void launch_sub(double* out, const double* a, const double* b, int64_t n, cudaStream_t s);
+// dense lower-triangular L (N x N, ld N) from packed
+void launch_unpack_lower(Packed L, int64_t N, double* out, cudaStream_t s);
+// out[N x S] = L * z   (z: N x S, ld Np) -- used by sb_rand
+void launch_trmv_lower(Packed L, int64_t N, const double* z, double* out, int S, cudaStream_t s);
+
+extern thread_local int64_t g_launch_count;
+
+}  // namespace sb

@@ -1,0 +1,160 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances: fp64, rtol 1e-10 on logpdf / posterior (BASELINE.json north_star); covariance
+entries to 1e-13 absolute (1-D inputs follow the reference's rounding sequence exactly, so they
+are in practice bit-identical up to the ulp of exp()).
+"""
+import numpy as np
+import pytest
+
+from models import f3_model, mixing_model, rich_model, toy_model
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def both(sb, orc, builder):
+    return builder(sb), builder(orc)
+
+
+def test_cov_single_kernels(sb, orc):
+    rng = np.random.default_rng(1)
+    x, y = rng.uniform(0, 8, 301), rng.uniform(0, 8, 77)
+    for name in ["SEKernel", "Matern12Kernel", "Matern32Kernel", "Matern52Kernel", "WhiteKernel"]:
+        fs = sb.gppp(lambda GP: dict(f=GP(getattr(sb, name)())))
+        fo = orc.gppp(lambda GP: dict(f=GP(getattr(orc, name)())))
+        xs = np.concatenate([x, x[:5]])  # coincident points: k == 1 exactly
+        K = sb.cov(fs, sb.GPPPInput("f", xs))
+        Ko = orc.cov(fo, orc.GPPPInput("f", xs))
+        np.testing.assert_allclose(K, Ko, rtol=0, atol=1e-14)
+        assert np.all(np.diag(K) == 1.0)
+        assert K[0, 301] == 1.0
+        Kxy = sb.cov(fs, sb.GPPPInput("f", x), sb.GPPPInput("f", y))
+        np.testing.assert_allclose(Kxy, orc.cov(fo, orc.GPPPInput("f", x), orc.GPPPInput("f", y)), rtol=0, atol=1e-14)
+        v = sb.var(fs, sb.GPPPInput("f", x))
+        np.testing.assert_array_equal(v, np.ones_like(x))
+
+
+def test_cov_large_offsets_bitwise_formula(sb, orc):
+    """x ~ U(0, 2048): the GEMM-trick distance loses ~1e-9 absolute in d^2; the device must
+    follow the same rounding sequence as the CPU path, not the (more accurate) direct form."""
+    rng = np.random.default_rng(2)
+    x = rng.uniform(0, 2048, 500)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    K, Ko = sb.cov(fs, sb.GPPPInput("f", x)), orc.cov(fo, orc.GPPPInput("f", x))
+    np.testing.assert_allclose(K, Ko, rtol=4e-16, atol=1e-300)
+
+
+def test_cov_gppp_blocks(sb, orc):
+    rng = np.random.default_rng(3)
+    xs = [rng.uniform(-3, 3, n) for n in (130, 61, 259)]
+    for builder, names in [(f3_model, ["f1", "f2", "f3"]), (toy_model, ["f3", "f1", "f2"]),
+                           (rich_model, ["g1", "g4", "g3"]), (mixing_model, ["g1", "g5", "g3"])]:
+        fs, fo = both(sb, orc, builder)
+        bs = sb.BlockData(*[sb.GPPPInput(n, x) for n, x in zip(names, xs)])
+        bo = orc.BlockData(*[orc.GPPPInput(n, x) for n, x in zip(names, xs)])
+        K, Ko = sb.cov(fs, bs), orc.cov(fo, bo)
+        np.testing.assert_allclose(K, Ko, rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(sb.var(fs, bs), orc.var(fo, bo), rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(sb.mean(fs, bs), orc.mean(fo, bo), rtol=1e-14, atol=1e-15)
+        # cross-covariance between different input collections / processes
+        b2s, b2o = sb.GPPPInput(names[0], xs[1]), orc.GPPPInput(names[0], xs[1])
+        np.testing.assert_allclose(sb.cov(fs, bs, b2s), orc.cov(fo, bo, b2o), rtol=1e-13, atol=1e-14)
+
+
+def test_cov_multidim(sb, orc):
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((3, 150))
+    def build(m):
+        return m.gppp(lambda GP: (lambda a, b: dict(a=a, b=b, c=m.additive_gp([a, b], [[0, 1], [2]]),
+                                                    d=m.stretch(a, np.array([[1., .2, 0], [0, .5, .1]]))))(
+            GP(m.SEKernel()), GP(m.Matern32Kernel())))
+    fs, fo = build(sb), build(orc)
+    for name in ["a", "c", "d"]:
+        K = sb.cov(fs, sb.GPPPInput(name, sb.ColVecs(X)))
+        Ko = orc.cov(fo, orc.GPPPInput(name, orc.ColVecs(X)))
+        np.testing.assert_allclose(K, Ko, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("n", [1, 5, 128, 129, 300, 1000])
+def test_cholesky_factor(sb, n):
+    import scipy.linalg as sla
+    rng = np.random.default_rng(n)
+    x = np.sort(rng.uniform(0, n / 32 + 1, n))
+    fs = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel())))
+    fx = fs(sb.GPPPInput("f", x), 0.1)
+    L = fx.factor().to_dense_L()
+    K = sb.cov(fx)
+    Lref = sla.cholesky(K, lower=True)
+    np.testing.assert_allclose(L, Lref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(fx.factor().logdet(), 2 * np.sum(np.log(np.diag(Lref))), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,ns", [(256, 256), (1000, 333), (4096, 512)])
+def test_logpdf_posterior_se(sb, orc, n, ns):
+    """Config 1 (N=256) and larger: logpdf + posterior mean/var, rtol 1e-10."""
+    rng = np.random.default_rng(123456)
+    x = np.sort(rng.uniform(0, n / 32, n))
+    xs = rng.uniform(0, n / 32, ns)
+    y = np.sin(x) + 0.3 * rng.standard_normal(n)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    fxs, fxo = fs(sb.GPPPInput("f", x), 0.1), fo(orc.GPPPInput("f", x), 0.1)
+    lp, lpo = sb.logpdf(fxs, y), orc.logpdf(fxo, y)
+    np.testing.assert_allclose(lp, lpo, rtol=RTOL)
+    Y = np.stack([y, y[::-1], 2 * y], axis=1)
+    np.testing.assert_allclose(sb.logpdf(fxs, Y), orc.logpdf(fxo, Y), rtol=RTOL)
+    ps, po = sb.posterior(fxs, y), orc.posterior(fxo, y)
+    np.testing.assert_allclose(ps.alpha, po.alpha, rtol=1e-8, atol=1e-9)
+    m, v = sb.mean_and_var(ps, sb.GPPPInput("f", xs))
+    mo, vo = orc.mean_and_var(po, orc.GPPPInput("f", xs))
+    np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(v, vo, rtol=RTOL, atol=1e-11)
+    mm, sd = sb.marginals(ps(sb.GPPPInput("f", xs), 0.01))
+    np.testing.assert_allclose(sd, np.sqrt(vo + 0.01), rtol=RTOL)
+
+
+def test_logpdf_posterior_gppp(sb, orc):
+    """Config-3 shaped: observe f1, f2, f3 = f1 + f2 jointly, predict all three."""
+    rng = np.random.default_rng(7)
+    ns = (700, 513, 300)
+    xs = [rng.uniform(0, 20, n) for n in ns]
+    xp = [rng.uniform(0, 20, 90) for _ in range(3)]
+    fs, fo = both(sb, orc, f3_model)
+    names = ["f1", "f2", "f3"]
+    bs, bo = sb.BlockData(*[sb.GPPPInput(n, x) for n, x in zip(names, xs)]), orc.BlockData(*[orc.GPPPInput(n, x) for n, x in zip(names, xs)])
+    ps_in, po_in = sb.BlockData(*[sb.GPPPInput(n, x) for n, x in zip(names, xp)]), orc.BlockData(*[orc.GPPPInput(n, x) for n, x in zip(names, xp)])
+    fxo = fo(bo, 0.1)
+    y = orc.rand(fxo, rng.standard_normal(sum(ns)))
+    fxs = fs(bs, 0.1)
+    np.testing.assert_allclose(sb.logpdf(fxs, y), orc.logpdf(fxo, y), rtol=RTOL)
+    ps, po = sb.posterior(fxs, y), orc.posterior(fxo, y)
+    m, v = sb.mean_and_var(ps, ps_in)
+    mo, vo = orc.mean_and_var(po, po_in)
+    np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(v, vo, rtol=1e-9, atol=1e-10)
+    C = sb.cov(ps, ps_in)
+    np.testing.assert_allclose(C, orc.cov(po, po_in), rtol=1e-9, atol=1e-10)
+    parts = sb.split(ps_in, m)
+    assert [len(p) for p in parts] == [90, 90, 90]
+
+
+def test_rich_model_logpdf_vector_noise(sb, orc):
+    rng = np.random.default_rng(8)
+    fs, fo = both(sb, orc, rich_model)
+    xs = [rng.uniform(-2, 2, n) for n in (200, 150, 141)]
+    names = ["g4", "g3", "f2"]
+    bs, bo = sb.BlockData(*[sb.GPPPInput(n, x) for n, x in zip(names, xs)]), orc.BlockData(*[orc.GPPPInput(n, x) for n, x in zip(names, xs)])
+    noise = rng.uniform(0.05, 0.2, 491)
+    fxs, fxo = fs(bs, noise), fo(bo, noise)
+    y = orc.rand(fxo, rng.standard_normal(491))
+    np.testing.assert_allclose(sb.logpdf(fxs, y), orc.logpdf(fxo, y), rtol=RTOL)
+    ys = sb.rand(fxs, np.ones(491))
+    np.testing.assert_allclose(ys, orc.rand(fxo, np.ones(491)), rtol=1e-9, atol=1e-9)
+
+
+def test_not_positive_definite(sb):
+    x = np.concatenate([np.linspace(0, 1, 200), np.linspace(0, 1, 200)])  # duplicated points, no noise
+    fs = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel())))
+    with pytest.raises(sb.PosDefException) as ei:
+        sb.logpdf(fs(sb.GPPPInput("f", x), 0.0), np.zeros(400))
+    assert 1 <= ei.value.info <= 400
