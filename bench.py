@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the dense-GP hot path (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  assemble K (SE kernel, N=65536 1-D inputs, fp64) -> Cholesky(K + 0.1 I) -> logpdf(y)
+  -> posterior mean & variance at N*=4096 test points.
+`value`  = N / step time with inputs already resident in HBM (device pointers through the C ABI),
+           timed with CUDA events on the library's own stream (max over ranks).
+`e2e`    = the same through the public API with HOST numpy buffers (H2D/D2H inside the region).
+`--impl reference` times the CPU restatement of the reference path (oracle fast path:
+  NumPy + SciPy/OpenBLAS, all host threads) on a bounded sample and extrapolates with the
+  N^3 / N^2 cost model (the reference is Julia; no julia binary in this image -- DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_TRAIN = 65536
+N_TEST = 4096
+SIGMA2 = 0.1
+DMMA_PEAK_TFLOPS = 37.1  # builder-measured, tools/mb_fp64_peak.cu on this pool's B200 (profiles/)
+
+
+def make_inputs(n, ns):
+    """x ~ U(0, n/32) (32 points per length-scale), y = sin(x)+0.3 eps."""
+    rng = np.random.default_rng(123456)
+    x = rng.uniform(0, n / 32, n)
+    xs = rng.uniform(0, n / 32, ns)
+    y = np.sin(x) + 0.3 * rng.standard_normal(n)
+    return x, y, xs
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: oracle fast path (same LAPACK entry points as Julia+OpenBLAS)
+# ------------------------------------------------------------------------------------------
+
+
+def cpu_pipeline(x, y, xs, sigma2):
+    """Fast-path restatement used for timing; numerically identical to
+    oracle/stheno_oracle.py's logpdf + posterior for a single SE process (checked in tests)."""
+    import scipy.linalg as sla
+    from oracle.stheno_oracle import pairwise_sqeuclidean
+    t = {}
+    t0 = time.perf_counter()
+    K = pairwise_sqeuclidean(x.reshape(1, -1))
+    np.multiply(K, -0.5, out=K)
+    np.exp(K, out=K)
+    K[np.diag_indices_from(K)] += sigma2
+    K = np.asfortranarray(K)
+    t["assemble"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    U = sla.cholesky(K, lower=False, overwrite_a=True, check_finite=False)
+    t["chol"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n = len(x)
+    v = sla.solve_triangular(U, y, trans="T", lower=False, check_finite=False)
+    lp = -(n * math.log(2 * math.pi) + 2 * np.sum(np.log(np.diag(U))) + v @ v) / 2
+    alpha = sla.solve_triangular(U, v, lower=False, check_finite=False)
+    t["solve"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Kfs = np.exp(-0.5 * pairwise_sqeuclidean(x.reshape(1, -1), xs.reshape(1, -1)))
+    mean = Kfs.T @ alpha
+    V = sla.solve_triangular(U, np.asfortranarray(Kfs), trans="T", lower=False, overwrite_b=True,
+                             check_finite=False)
+    var = 1.0 - np.einsum("ij,ij->j", V, V)
+    t["posterior"] = time.perf_counter() - t0
+    return lp, mean, var, t
+
+
+def cpu_extrapolate(t, n_s, ns_s, n, ns):
+    """Scale measured phase times from the sample (n_s, ns_s) to (n, ns)."""
+    r = n / n_s
+    return (t["assemble"] * r * r + t["chol"] * r ** 3 + t["solve"] * r * r
+            + t["posterior"] * r * r * (ns / ns_s))
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_sample(n_s=None, reps=1):
+    cores = cpu_threads()
+    if n_s is None:
+        n_s = 8192 if cores <= 16 else 12288
+    ns_s = max(64, n_s // 16)
+    x, y, xs = make_inputs(n_s, ns_s)
+    best = None
+    for _ in range(reps):
+        _, _, _, t = cpu_pipeline(x, y, xs, SIGMA2)
+        tot = sum(t.values())
+        if best is None or tot < sum(best.values()):
+            best = t
+    measured = sum(best.values())
+    ext = cpu_extrapolate(best, n_s, ns_s, N_TRAIN, N_TEST)
+    return dict(n_sample=n_s, ns_sample=ns_s, measured_s=measured, extrapolated_s=ext, phases=best,
+                cores=cores)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        # "under load" = samples drawing more than half of the max observed power
+        load = [s for s, p in zip(sm, pw) if pw and p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+
+
+def gpu_main(args):
+    import ctypes as C
+
+    import torch
+    import stheno_jl_b200 as sb
+    from stheno_jl_b200 import lib as sblib
+    from stheno_jl_b200.gp import Lowered, spec_dense, spec_diag, spec_symmetric
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+        ids = [sblib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = sblib.Context(local, rank, world, ids[0])
+    else:
+        ctx = sblib.Context(local)
+    sblib.set_default_context(ctx)
+    lib = sblib.load()
+
+    n, ns = args.n, args.ns
+    x, y, xs = make_inputs(n, ns)
+    f = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel())))
+
+    # ---- device-resident arm: inputs live in HBM before the timed region -----------------------
+    dev = torch.device("cuda", local)
+    xd, yd, xsd = (torch.from_numpy(a).to(dev) for a in (x, y, xs))
+    mean_d = torch.empty(ns, dtype=torch.float64, device=dev)
+    var_d = torch.empty(ns, dtype=torch.float64, device=dev)
+    lx = Lowered(f, sb.GPPPInput("f", xd))
+    ls = Lowered(f, sb.GPPPInput("f", xsd))
+    spec_k, spec_c, spec_d = spec_symmetric(lx), spec_dense(ls, lx), spec_diag(ls)
+    noise = sblib.sb_noise()
+    noise.sigma2, noise.diag = SIGMA2, None
+    lp_out = (C.c_double * 1)()
+
+    def device_step():
+        h = C.c_void_p()
+        info = C.c_int64(0)
+        sblib.check(lib.sb_factor_create(ctx.h, C.byref(spec_k), C.byref(noise), C.byref(h), C.byref(info)), info)
+        try:
+            sblib.check(lib.sb_logpdf(ctx.h, h, yd.data_ptr(), 1, lp_out))           # zero-mean: delta = y
+            sblib.check(lib.sb_factor_set_data(ctx.h, h, yd.data_ptr()))
+            sblib.check(lib.sb_predict(ctx.h, h, C.byref(spec_c), C.byref(spec_d), mean_d.data_ptr(), var_d.data_ptr()))
+        finally:
+            lib.sb_factor_destroy(h)
+        return lp_out[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    ctx.timings(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # The library runs on its own stream and every ABI call is synchronous; the device time of a
+    # step is the sum of the CUDA-event phase timers the library records on that stream
+    # (sb_timings.total_ms), cross-checked against the host wall clock around the same calls.
+    t0 = time.perf_counter()
+    ctx.mark(0)
+    for _ in range(args.steps):
+        lp = device_step()
+    ctx.mark(1)
+    dev_ms = ctx.elapsed_ms(0, 1)  # CUDA events on the launching (library) stream around K steps
+    torch.cuda.synchronize()
+    wall_dev = time.perf_counter() - t0
+    tm = ctx.timings()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = dev_ms / args.steps
+    if dist is not None:
+        tt = torch.tensor([step_ms, wall_dev * 1e3 / args.steps], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_ms, wall_ms = tt.tolist()
+    else:
+        wall_ms = wall_dev * 1e3 / args.steps
+
+    # ---- end-to-end arm: public API, host numpy buffers in, host numpy out ---------------------
+    def e2e_step():
+        fx = f(sb.GPPPInput("f", x), SIGMA2)
+        lp = sb.logpdf(fx, y)
+        post = sb.posterior(fx, y)
+        m, v = sb.mean_and_var(post, sb.GPPPInput("f", xs))
+        return lp, m, v
+
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        lp_e, m_e, v_e = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        tt = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = tt.item()
+    h2d = 8 * (n + n + n + ns + n)  # x (factor), delta (logpdf), delta (posterior), x*, x (cross spec)
+    d2h = 8 * (2 * ns + 1)
+
+    if rank != 0:
+        return
+    np.testing.assert_allclose(mean_d.cpu().numpy(), m_e, rtol=1e-9, atol=1e-10)
+
+    # ---- roofline of the dominant kernel (DMMA trailing update) ----------------------------------
+    ach = tm["trailing_flops"] / (tm["trailing_kernel_ms"] * 1e-3) / 1e12 if tm["trailing_kernel_ms"] else None
+    roof = {"bound": "tensor", "kernel": "gemm_nt_kernel (fp64 DMMA SYRK trailing update)",
+            "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+            "frac": (ach / DMMA_PEAK_TFLOPS) if ach else None,
+            "peak_source": "builder-measured mma.sync m8n8k4 f64 microbenchmark (tools/mb_fp64_peak.cu, "
+                           "profiles/mb_fp64_peak_r1.txt); MEASURED_PEAKS.json has no fp64 entry, "
+                           "tcgen05 has no fp64 kind",
+            "launches": tm["trailing_launches"] // max(1, args.steps),
+            "flops_per_step": tm["trailing_flops"] / args.steps,
+            "traffic": None}
+    hbm_peak = 6575.8
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    asm_bytes = (n * (n + 1) / 2 * 8 + n * 8)
+    roof_asm = {"bound": "hbm", "kernel": "assemble_kernel<packed>", "achieved": asm_bytes / (tm["assemble_ms"] / args.steps * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s"}
+    roof_asm["frac"] = roof_asm["achieved"] / hbm_peak
+    phases = {k: tm[k] / args.steps for k in ("assemble_ms", "panel_ms", "trailing_ms", "comm_ms", "solve_ms", "predict_ms")}
+
+    cb = None
+    if args.gpus == 1 and not args.no_cpu:
+        s = run_cpu_sample()
+        cb = {"value": N_TRAIN / s["extrapolated_s"], "unit": "points/s", "cores": s["cores"], "kind": "port",
+              "sample": f"oracle fast path (NumPy+SciPy/OpenBLAS) measured at N={s['n_sample']}, N*={s['ns_sample']}: "
+                        f"{s['measured_s']:.2f} s; value extrapolated to N={N_TRAIN}, N*={N_TEST} with the "
+                        f"N^3 (chol) / N^2 (assemble, solves) / N^2 N* (posterior) model = {s['extrapolated_s']:.0f} s",
+              "phases_s": s["phases"]}
+
+    out = {
+        "metric": "logpdf+posterior points/sec, N=65536 SE-GP fp64", "value": n / (step_ms * 1e-3),
+        "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "wall_ms_per_step": wall_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config 2: SEKernel GP N={n} fp64, 1-D inputs U(0,N/32), sigma2=0.1: "
+                               f"kernelmatrix + Cholesky logpdf + posterior mean/var at N*={ns}",
+                   "n_train": n, "n_test": ns, "l2": "inputs >> L2 (17.2 GB factor; no flush needed)",
+                   "parallelism": f"1-D block-cyclic columns x{args.gpus}, NCCL panel broadcast" if args.gpus > 1 else "single GPU"},
+        "e2e": {"value": n / e2e_s, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": tm["kernel_launches"], "roofline": roof, "roofline_assemble": roof_asm,
+        "phases_ms": phases, "logpdf": lp, "clocks": clocks,
+    }
+    if cb:
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = []
+    for _ in range(max(1, args.warmup > 0)):
+        run_cpu_sample()
+    for _ in range(max(1, min(args.steps, 3))):
+        reps.append(run_cpu_sample())
+    ext = float(np.mean([r["extrapolated_s"] for r in reps]))
+    s = reps[-1]
+    val = N_TRAIN / ext
+    out = {
+        "impl": "reference", "metric": "logpdf+posterior points/sec, N=65536 SE-GP fp64", "value": val,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": len(reps), "warmup": args.warmup,
+        "ms_per_step": ext * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config 2: SEKernel GP N={N_TRAIN} fp64: kernelmatrix + Cholesky logpdf + "
+                               f"posterior mean/var at N*={N_TEST} (CPU restatement of the reference path; "
+                               "Julia is not installed in this image)"},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": s["cores"], "kind": "port",
+                         "sample": f"each step = oracle fast path at N={s['n_sample']}, N*={s['ns_sample']} "
+                                   f"({s['measured_s']:.2f} s measured), extrapolated to N={N_TRAIN} by the "
+                                   "N^3/N^2 cost model"},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_TRAIN)
+    ap.add_argument("--ns", type=int, default=N_TEST)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_main(args)
+    else:
+        gpu_main(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,10 @@ int32_t sb_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const vo
                            sb_ctx** out);
 int32_t sb_ctx_destroy(sb_ctx* ctx);
 int32_t sb_ctx_timings(sb_ctx* ctx, sb_timings* out, int32_t reset);
+/* benchmark support: record a CUDA event on the library's stream into slot 0..7 / read the
+ * elapsed device time between two recorded slots (synchronises on the later one). */
+int32_t sb_ctx_mark(sb_ctx* ctx, int32_t slot);
+int32_t sb_ctx_elapsed_ms(sb_ctx* ctx, int32_t slot_a, int32_t slot_b, double* ms);
 
 /* ---- covariance assembly ---------------------------------------------------------------
  * sb_cov_dense replaces  cov(f::GPPP, x[, x'])  -> Matrix

@@ -1,5 +1,6 @@
 // C ABI of libstheno_b200 (see include/stheno_b200.h): contexts, plan upload, the blocked
 // right-looking Cholesky driver, logpdf / posterior / rand / VFE orchestration.
+#include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
 #include <stdlib.h>
@@ -28,11 +29,50 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 using namespace sb;
 
+// NCCL is bound lazily with dlopen (only when world > 1): a single-GPU / Julia user never loads
+// it, and inside a Python process that also imports torch the already-loaded libnccl.so.2
+// (torch bundles its own) is reused instead of clashing with the system copy.
+namespace nccl_dl {
+typedef ncclResult_t (*GetUniqueId_t)(ncclUniqueId*);
+typedef ncclResult_t (*CommInitRank_t)(ncclComm_t*, int, ncclUniqueId, int);
+typedef ncclResult_t (*CommDestroy_t)(ncclComm_t);
+typedef ncclResult_t (*Broadcast_t)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*AllReduce_t)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*Group_t)(void);
+typedef const char* (*ErrStr_t)(ncclResult_t);
+static GetUniqueId_t GetUniqueId;
+static CommInitRank_t CommInitRank;
+static CommDestroy_t CommDestroy;
+static Broadcast_t Broadcast;
+static AllReduce_t AllReduce;
+static Group_t GroupStart, GroupEnd;
+static ErrStr_t GetErrorString;
+static bool loaded = false;
+static bool load() {
+    if (loaded) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        sb::set_error(std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+        return false;
+    }
+#define SB_SYM(name) name = (name##_t)dlsym(h, "nccl" #name); if (!name) { sb::set_error("missing NCCL symbol nccl" #name); return false; }
+    SB_SYM(GetUniqueId) SB_SYM(CommInitRank) SB_SYM(CommDestroy) SB_SYM(Broadcast) SB_SYM(AllReduce)
+    GroupStart = (Group_t)dlsym(h, "ncclGroupStart");
+    GroupEnd = (Group_t)dlsym(h, "ncclGroupEnd");
+    GetErrorString = (ErrStr_t)dlsym(h, "ncclGetErrorString");
+    if (!GroupStart || !GroupEnd || !GetErrorString) { sb::set_error("missing NCCL group symbols"); return false; }
+#undef SB_SYM
+    loaded = true;
+    return true;
+}
+}  // namespace nccl_dl
+
 #define SB_NCCL(call)                                                                   \
     do {                                                                                \
         ncclResult_t _r = (call);                                                       \
         if (_r != ncclSuccess) {                                                        \
-            sb::set_error(std::string("NCCL error: ") + ncclGetErrorString(_r) + " in " #call); \
+            sb::set_error(std::string("NCCL error: ") + nccl_dl::GetErrorString(_r) + " in " #call); \
             return SB_ERR_NCCL;                                                         \
         }                                                                               \
     } while (0)
@@ -45,6 +85,7 @@ struct sb_ctx {
     cudaStream_t stream2 = nullptr;  // look-ahead panel stream (multi-GPU)
     sb_timings tm{};
     bool fine_timing = true;
+    cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev;
     size_t ev_used = 0;
     cudaEvent_t next_event() {
@@ -198,70 +239,89 @@ int32_t assemble_diag(sb_ctx* c, DevSpec& ds, double* out) {
 }
 
 // ---- blocked right-looking Cholesky on the packed matrix ----------------------------------
-// step k:  L_kk = chol(A_kk), Linv_kk            (potrf.cu, one CTA)
-//          P    = A[k+1:, k] * Linv_kk^T          (gemm_nt.cu, DMMA)   -> panel buffer
-//          [multi-GPU: ncclBroadcast(P) from the owner of block column k]
-//          A[I, J] -= P_I P_J^T,  k < J <= I       (gemm_nt.cu, DMMA, owned block columns)
-// Block column J is owned by rank J % world (1-D block-cyclic); after the sweep every rank
-// holds the complete factor (received panels are kept), so solves need no communication.
+// Two-level blocking: the layout / diagonal-block size is NB = 128, but trailing updates are
+// applied for TWO block columns at once (K = 256), which halves the C read-modify-write traffic
+// and the per-tile prologue/epilogue share of the DMMA kernel.  Outer step (k0, k1 = k0+1):
+//   L_00 = chol(A_00), Linv_00                         (potrf.cu, one CTA)
+//   P1   = A[k0+1:, k0] * Linv_00^T                    (gemm_nt.cu)      -> Pc[:, 0:128]
+//   A[:, k1] -= P1 * P1_k1^T                            (gemm_nt.cu, one block column, K = 128)
+//   L_11 = chol(A_11), Linv_11 ; P2 = A[k1+1:, k1] * Linv_11^T          -> Pc[128:, 128:256]
+//   A[I, J] -= Pc_I * Pc_J^T,  k1 < J <= I              (gemm_nt.cu, K = 256, owned columns)
+// Multi-GPU: block column J is owned by rank J % world (1-D block-cyclic); each half panel is
+// broadcast by its owner with ncclBroadcast, received panels are kept, so after the sweep every
+// rank holds the complete factor and the solves need no communication.
+struct CholEv { cudaEvent_t e[4]; };
+
+static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, size_t slab_elems, int owner) {
+    cudaStream_t st = c->stream;
+    SB_NCCL(nccl_dl::GroupStart());
+    SB_NCCL(nccl_dl::Broadcast(f->invL + k * (int64_t)NB * NB, f->invL + k * (int64_t)NB * NB,
+                               (size_t)NB * NB, ncclDouble, owner, c->comm, st));
+    SB_NCCL(nccl_dl::Broadcast(f->logdet_blk + k, f->logdet_blk + k, 1, ncclDouble, owner, c->comm, st));
+    if (slab_elems) SB_NCCL(nccl_dl::Broadcast(Pslab, Pslab, slab_elems, ncclDouble, owner, c->comm, st));
+    SB_NCCL(nccl_dl::GroupEnd());
+    return SB_OK;
+}
+
 int32_t cholesky_packed(sb_ctx* c, sb_factor* f) {
     const int64_t nblk = f->L.nblk();
     const int64_t Np = f->Np;
     cudaStream_t st = c->stream;
-    struct StepEv { cudaEvent_t a, b, c, d; };
-    std::vector<StepEv> sev;
-    if (c->fine_timing) sev.resize(nblk);
+    const bool ft = c->fine_timing;
+    std::vector<cudaEvent_t> ev;  // per outer step: t0, after panel work, after comm, after trailing ...
+    auto mark = [&]() {
+        if (ft) {
+            cudaEvent_t e = c->next_event();
+            cudaEventRecord(e, st);
+            ev.push_back(e);
+        }
+    };
+    std::vector<int> evkind;  // kind of the interval ENDING at event i: 0 panel, 1 comm, 2 trailing(big), 3 start
+    auto markk = [&](int kind) { if (ft) { mark(); evkind.push_back(kind); } };
     double flops = 0;
     int64_t nlaunch = 0;
-    for (int64_t k = 0; k < nblk; k++) {
-        const int owner = (int)(k % c->world);
-        const int64_t m = Np - (k + 1) * NB;
-        double* P = f->panel + (k & 1) * (Np * (int64_t)NB);
-        if (c->fine_timing) {
-            sev[k].a = c->next_event();
-            cudaEventRecord(sev[k].a, st);
+    double* Pc = f->panel;
+    for (int64_t k0 = 0; k0 < nblk; k0 += 2) {
+        const int64_t k1 = k0 + 1;
+        const int64_t m0 = Np - (k0 + 1) * NB;
+        const int own0 = (int)(k0 % c->world), own1 = (int)(k1 % c->world);
+        markk(3);
+        if (own0 == c->rank) {
+            launch_potrf_inv(f->L, k0, f->N, f->invL, f->logdet_blk, f->info_dev, st);
+            if (m0 > 0)
+                launch_gemm_nt(f->L.blk(k0 + 1, k0), f->L.ld(k0), f->invL + k0 * (int64_t)NB * NB, NB, Pc, m0,
+                               m0, NB, NB, 1.0, 0.0, st);
         }
-        if (owner == c->rank) {
-            launch_potrf_inv(f->L, k, f->N, f->invL, f->logdet_blk, f->info_dev, st);
-            if (m > 0) {
-                launch_gemm_nt(f->L.blk(k + 1, k), f->L.ld(k), f->invL + k * (int64_t)NB * NB, NB, P, m,
-                               m, NB, NB, 1.0, 0.0, st);
-            }
+        markk(0);
+        if (c->world > 1) SB_TRY(bcast_panel(c, f, k0, Pc, (size_t)m0 * NB, own0));
+        markk(1);
+        if (m0 <= 0) break;
+        SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k0 + 1, k0), f->L.ld(k0) * sizeof(double), Pc, m0 * sizeof(double),
+                                  m0 * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+        // second half panel: block column k1 gets the k0 update first, then is factored
+        const int64_t m1 = m0 - NB;
+        double* P2 = Pc + (int64_t)NB * m0 + NB;  // column 128, row offset 128 (row 0 <-> block row k1)
+        if (own1 == c->rank) {
+            launch_syrk_packed(f->L, k0, Pc, NB, k1, k1 + 1, c->rank, c->world, st);
+            launch_potrf_inv(f->L, k1, f->N, f->invL, f->logdet_blk, f->info_dev, st);
+            if (m1 > 0)
+                launch_gemm_nt(f->L.blk(k1 + 1, k1), f->L.ld(k1), f->invL + k1 * (int64_t)NB * NB, NB, P2, m0,
+                               m1, NB, NB, 1.0, 0.0, st);
         }
-        if (c->fine_timing) {
-            sev[k].b = c->next_event();
-            cudaEventRecord(sev[k].b, st);
-        }
-        if (c->world > 1) {
-            // broadcast diagonal block inverse + L_kk (small) and the panel
-            SB_NCCL(ncclGroupStart());
-            SB_NCCL(ncclBroadcast(f->invL + k * (int64_t)NB * NB, f->invL + k * (int64_t)NB * NB,
-                                  (size_t)NB * NB, ncclDouble, owner, c->comm, st));
-            SB_NCCL(ncclBroadcast(f->logdet_blk + k, f->logdet_blk + k, 1, ncclDouble, owner, c->comm, st));
-            if (m > 0) SB_NCCL(ncclBroadcast(P, P, (size_t)m * NB, ncclDouble, owner, c->comm, st));
-            SB_NCCL(ncclGroupEnd());
-        }
-        if (m > 0) {
-            // keep the factored panel in the matrix on every rank (complete L everywhere)
-            SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k + 1, k), f->L.ld(k) * sizeof(double), P,
-                                      m * sizeof(double), m * sizeof(double), NB,
-                                      cudaMemcpyDeviceToDevice, st));
-        }
-        if (c->fine_timing) {
-            sev[k].c = c->next_event();
-            cudaEventRecord(sev[k].c, st);
-        }
-        if (m > 0) {
-            int64_t tiles = syrk_packed_tiles(nblk, k, k + 1, nblk, c->rank, c->world);
-            launch_syrk_packed(f->L, k, P, k + 1, nblk, c->rank, c->world, st);
+        markk(0);
+        if (c->world > 1) SB_TRY(bcast_panel(c, f, k1, Pc + (int64_t)NB * m0, m1 > 0 ? (size_t)m0 * NB : 0, own1));
+        markk(1);
+        if (m1 > 0) {
+            SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k1 + 1, k1), f->L.ld(k1) * sizeof(double), P2, m0 * sizeof(double),
+                                      m1 * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+            int64_t tiles = syrk_packed_tiles(nblk, k0, k1 + 1, nblk, c->rank, c->world);
+            markk(0);
+            launch_syrk_packed(f->L, k0, Pc, 2 * NB, k1 + 1, nblk, c->rank, c->world, st);
+            markk(2);
             if (tiles > 0) {
-                flops += (double)tiles * 2.0 * NB * NB * NB;
+                flops += (double)tiles * 2.0 * NB * NB * (2.0 * NB);
                 nlaunch++;
             }
-        }
-        if (c->fine_timing) {
-            sev[k].d = c->next_event();
-            cudaEventRecord(sev[k].d, st);
         }
     }
     if (c->world > 1) {
@@ -269,30 +329,37 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f) {
         // rank holds the complete factor (needed by the replicated / RHS-sharded solves)
         for (int64_t k = 0; k < nblk; k++) {
             int owner = (int)(k % c->world);
-            // L_kk is the top NB rows of block column k: NB columns of NB rows, strided by ld(k).
-            // Pack through the panel buffer.
-            double* tmp = f->panel;
+            double* tmp = f->panel;  // pack L_kk (NB columns strided by ld(k)) through the panel buffer
             if (owner == c->rank)
                 SB_CUDA(cudaMemcpy2DAsync(tmp, NB * sizeof(double), f->L.blk(k, k), f->L.ld(k) * sizeof(double),
                                           NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
-            SB_NCCL(ncclBroadcast(tmp, tmp, (size_t)NB * NB, ncclDouble, owner, c->comm, st));
+            SB_NCCL(nccl_dl::Broadcast(tmp, tmp, (size_t)NB * NB, ncclDouble, owner, c->comm, st));
             if (owner != c->rank)
                 SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k, k), f->L.ld(k) * sizeof(double), tmp, NB * sizeof(double),
                                           NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
         }
+        // first failing pivot over all ranks: min over ranks of (info ? info : INT64_MAX)
+        long long h = 0;
+        SB_CUDA(cudaMemcpyAsync(&h, f->info_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (h == 0) h = 0x7fffffffffffffffLL;
+        SB_CUDA(cudaMemcpyAsync(f->info_dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+        SB_NCCL(nccl_dl::AllReduce(f->info_dev, f->info_dev, 1, ncclInt64, ncclMin, c->comm, st));
+        SB_CUDA(cudaMemcpyAsync(&h, f->info_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (h == 0x7fffffffffffffffLL) h = 0;
+        SB_CUDA(cudaMemcpyAsync(f->info_dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     }
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaStreamSynchronize(st));
-    if (c->fine_timing) {
-        for (int64_t k = 0; k < nblk; k++) {
-            float t1, t2, t3;
-            cudaEventElapsedTime(&t1, sev[k].a, sev[k].b);
-            cudaEventElapsedTime(&t2, sev[k].b, sev[k].c);
-            cudaEventElapsedTime(&t3, sev[k].c, sev[k].d);
-            c->tm.panel_ms += t1;
-            c->tm.comm_ms += t2;
-            c->tm.trailing_ms += t3;
-            c->tm.trailing_kernel_ms += t3;
+    if (ft) {
+        for (size_t i = 1; i < ev.size(); i++) {
+            if (evkind[i] == 3) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            if (evkind[i] == 0) c->tm.panel_ms += ms;
+            else if (evkind[i] == 1) c->tm.comm_ms += ms;
+            else { c->tm.trailing_ms += ms; c->tm.trailing_kernel_ms += ms; }
         }
     }
     c->tm.trailing_flops += flops;
@@ -368,7 +435,8 @@ int32_t sb_nccl_unique_id(void* id128) {
     SB_CHECK(id128 != nullptr, "null id");
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     ncclUniqueId id;
-    SB_NCCL(ncclGetUniqueId(&id));
+    if (!nccl_dl::load()) return SB_ERR_NCCL;
+    SB_NCCL(nccl_dl::GetUniqueId(&id));
     memcpy(id128, &id, 128);
     return SB_OK;
 }
@@ -384,7 +452,8 @@ int32_t sb_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const vo
         SB_CHECK(nccl_id128 != nullptr, "null nccl id");
         ncclUniqueId id;
         memcpy(&id, nccl_id128, 128);
-        SB_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+        if (!nccl_dl::load()) return SB_ERR_NCCL;
+        SB_NCCL(nccl_dl::CommInitRank(&c->comm, world, id, rank));
     }
     return SB_OK;
 }
@@ -392,8 +461,9 @@ int32_t sb_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const vo
 int32_t sb_ctx_destroy(sb_ctx* c) {
     if (!c) return SB_OK;
     cudaSetDevice(c->device);
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm) nccl_dl::CommDestroy(c->comm);
     for (auto e : c->ev) cudaEventDestroy(e);
+    for (auto e : c->marks) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
@@ -404,6 +474,23 @@ int32_t sb_ctx_timings(sb_ctx* c, sb_timings* out, int32_t reset) {
     SB_CHECK(c != nullptr, "null ctx");
     if (out) *out = c->tm;
     if (reset) c->tm = sb_timings{};
+    return SB_OK;
+}
+
+int32_t sb_ctx_mark(sb_ctx* c, int32_t slot) {
+    SB_CHECK(c && slot >= 0 && slot < 8, "bad mark slot");
+    cudaSetDevice(c->device);
+    if (!c->marks[slot]) SB_CUDA(cudaEventCreate(&c->marks[slot]));
+    SB_CUDA(cudaEventRecord(c->marks[slot], c->stream));
+    return SB_OK;
+}
+
+int32_t sb_ctx_elapsed_ms(sb_ctx* c, int32_t a, int32_t b, double* ms) {
+    SB_CHECK(c && ms && a >= 0 && a < 8 && b >= 0 && b < 8 && c->marks[a] && c->marks[b], "bad mark slot");
+    SB_CUDA(cudaEventSynchronize(c->marks[b]));
+    float f = 0;
+    SB_CUDA(cudaEventElapsedTime(&f, c->marks[a], c->marks[b]));
+    *ms = f;
     return SB_OK;
 }
 
@@ -489,7 +576,7 @@ int32_t sb_factor_create(sb_ctx* c, const sb_covspec* spec, const sb_noise* nois
     SB_CUDA_F(cudaMalloc(&f->invL, (size_t)nblk * NB * NB * sizeof(double)));
     SB_CUDA_F(cudaMalloc(&f->logdet_blk, (size_t)nblk * sizeof(double)));
     SB_CUDA_F(cudaMalloc(&f->info_dev, sizeof(long long)));
-    SB_CUDA_F(cudaMalloc(&f->panel, (size_t)2 * f->Np * NB * sizeof(double)));
+    SB_CUDA_F(cudaMalloc(&f->panel, (size_t)2 * f->Np * NB * sizeof(double)));  // Np x 256 panel pair
     SB_CUDA_F(cudaMalloc(&f->alpha, (size_t)f->Np * sizeof(double)));
     SB_CUDA_F(cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream));
     SB_CUDA_F(cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream));

@@ -146,7 +146,7 @@ assemble_kernel(BlockDev b, OutDense dense, Packed packed, int64_t N, double sig
         }
         bool in0 = (r0 >= b.row0 && r0 < rend), in1 = (r0 + 1 >= b.row0 && r0 + 1 < rend);
         double a0 = v[j][0], a1 = v[j][1];
-        if (PACKED) {
+        if (PACKED && !b.accumulate) {
             if (r0 == c) a0 += noise_diag ? noise_diag[c] : sigma2;
             if (r0 + 1 == c) a1 += noise_diag ? noise_diag[c] : sigma2;
         }

@@ -8,5 +8,5 @@ mkdir -p ../../build
 for f in assemble gemm_nt potrf solve api; do
   $NVCC $FLAGS -c $f.cu -o ../../build/$f.o 2> ../../build/$f.ptxas.log || { cat ../../build/$f.ptxas.log; exit 1; }
 done
-$NVCC -shared -o ../libstheno_b200.so ../../build/assemble.o ../../build/gemm_nt.o ../../build/potrf.o ../../build/solve.o ../../build/api.o -lnccl -lcudart
+$NVCC -shared -o ../libstheno_b200.so ../../build/assemble.o ../../build/gemm_nt.o ../../build/potrf.o ../../build/solve.o ../../build/api.o -lcudart -ldl
 echo "built $(cd ..; pwd)/libstheno_b200.so"

@@ -26,7 +26,7 @@ constexpr int STAGES = 4;
 constexpr int LDA_S = BM + 4;
 constexpr int LDB_S = BN + 4;
 constexpr int THREADS = 256;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * KC * (LDA_S + LDB_S) * 8 + STAGES * 8;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * KC * (LDA_S + LDB_S) * 8 + 2 * STAGES * 8;
 
 struct GemmArgs {
     int mode;  // 0 plain, 1 packed SYRK
@@ -37,6 +37,7 @@ struct GemmArgs {
     double* C;
     int64_t ldc;
     int64_t mtiles;  // plain: number of row tiles
+    int64_t total_tiles;
     int64_t K;
     double alpha, beta;
     // packed SYRK
@@ -100,127 +101,177 @@ __device__ __forceinline__ void decode_tri(int64_t t, int64_t nblk, int64_t J0, 
     I = J + (t - S(q));
 }
 
+struct TilePtrs {
+    const double* A;
+    const double* B;
+    double* C;
+    int64_t lda, ldb, ldc;
+};
+
+__device__ __forceinline__ TilePtrs tile_ptrs(const GemmArgs& g, int64_t tile) {
+    TilePtrs p;
+    if (g.mode == 0) {
+        int64_t rt = tile % g.mtiles, ct = tile / g.mtiles;
+        p.lda = g.lda; p.ldb = g.ldb; p.ldc = g.ldc;
+        p.A = g.A + rt * BM;
+        p.B = g.B + ct * BN;
+        p.C = g.C + ct * BN * g.ldc + rt * BM;
+    } else {
+        int64_t t = tile >> 1;
+        int h = (int)(tile & 1);
+        int64_t I, J;
+        decode_tri(t, g.Pk.nblk(), g.J0, g.w, I, J);
+        int64_t m = g.Pk.Np - (g.k + 1) * NB;  // panel rows (below the diagonal block of column k)
+        p.lda = p.ldb = m;
+        p.A = g.A + (I - g.k - 1) * NB;
+        p.B = g.A + (J - g.k - 1) * NB + h * BN;
+        p.ldc = g.Pk.ld(J);
+        p.C = g.Pk.blk(I, J) + (int64_t)h * BN * p.ldc;
+    }
+    return p;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent CTAs (2 per SM): each walks tiles blockIdx.x, +gridDim.x, ...  The operand ring is
+// addressed by a global chunk counter that runs ACROSS tiles, so the TMA engine is already
+// filling the next tile's first k-slabs while the warps are still in the current tile's
+// epilogue.  No CTA-wide barrier in the steady state: full[] (TMA -> warps, tx-count) and empty[]
+// (8 warps -> producer lane) mbarriers only.
 __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmArgs g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
     double* sB = sA + STAGES * KC * LDA_S;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * KC * LDB_S);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * KC * LDB_S);
+    uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
-
-    const double* Ag;
-    const double* Bg;
-    double* Cg;
-    int64_t lda, ldb, ldc;
-    if (g.mode == 0) {
-        int64_t t = blockIdx.x;
-        int64_t rt = t % g.mtiles, ct = t / g.mtiles;
-        lda = g.lda; ldb = g.ldb; ldc = g.ldc;
-        Ag = g.A + rt * BM;
-        Bg = g.B + ct * BN;
-        Cg = g.C + ct * BN * ldc + rt * BM;
-    } else {
-        int64_t t = blockIdx.x >> 1;
-        int h = blockIdx.x & 1;
-        int64_t I, J;
-        decode_tri(t, g.Pk.nblk(), g.J0, g.w, I, J);
-        int64_t m = g.Pk.Np - (g.k + 1) * NB;  // panel rows (below the diagonal block)
-        lda = ldb = m;
-        Ag = g.A + (I - g.k - 1) * NB;
-        Bg = g.A + (J - g.k - 1) * NB + h * BN;
-        ldc = g.Pk.ld(J);
-        Cg = g.Pk.blk(I, J) + (int64_t)h * BN * ldc;
-    }
-
     const int nchunks = (int)(g.K / KC);
+    const int64_t ntiles_cta = (g.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total_q = ntiles_cta * nchunks;
+
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], THREADS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int c) {  // warp 0, all lanes: one k-column of A or B per lane
-        int slot = c % STAGES;
-        if (lane == 0) mbar_expect_tx(&bars[slot], (BM + BN) * KC * 8);
+    // ---- producer state (warp 0 only) -------------------------------------------------------
+    int64_t pq = 0;          // next global chunk to issue
+    int pc = 0;              // its k-chunk inside the tile
+    TilePtrs pp = tile_ptrs(g, blockIdx.x);
+    int64_t ptile = blockIdx.x;
+    auto issue_next = [&]() {  // all lanes of warp 0
+        int slot = (int)(pq % STAGES);
+        if (lane == 0) mbar_expect_tx(&full[slot], (BM + BN) * KC * 8);
         __syncwarp();
         int kk = lane & 15;
-        int64_t kg = (int64_t)c * KC + kk;
+        int64_t kg = (int64_t)pc * KC + kk;
         if (lane < 16)
-            bulk_g2s(sA + (slot * KC + kk) * LDA_S, Ag + kg * lda, BM * 8, &bars[slot]);
+            bulk_g2s(sA + (slot * KC + kk) * LDA_S, pp.A + kg * pp.lda, BM * 8, &full[slot]);
         else
-            bulk_g2s(sB + (slot * KC + kk) * LDB_S, Bg + kg * ldb, BN * 8, &bars[slot]);
+            bulk_g2s(sB + (slot * KC + kk) * LDB_S, pp.B + kg * pp.ldb, BN * 8, &full[slot]);
+        pq++;
+        if (++pc == nchunks) {
+            pc = 0;
+            ptile += gridDim.x;
+            if (ptile < g.total_tiles) pp = tile_ptrs(g, ptile);
+        }
     };
-
     if (warp == 0) {
-        for (int c = 0; c < STAGES - 1 && c < nchunks; c++) issue(c);
+        for (int c = 0; c < STAGES - 1 && pq < total_q; c++) issue_next();
     }
-
-    double acc[4][4][2];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-        for (int i = 0; i < 4; i++) acc[j][i][0] = acc[j][i][1] = 0.0;
 
     const int wr = warp & 3, wc = warp >> 2;  // 4 warps along rows, 2 along cols; 32x32 each
-
-    for (int c = 0; c < nchunks; c++) {
-        int slot = c % STAGES;
-        mbar_wait(&bars[slot], (uint32_t)((c / STAGES) & 1));
-        __syncthreads();  // everyone is done with chunk c-1 -> its slot may be refilled
-        if (warp == 0 && c + STAGES - 1 < nchunks) issue(c + STAGES - 1);
-        const double* a = sA + slot * KC * LDA_S + wr * 32 + gid;
-        const double* b = sB + slot * KC * LDB_S + wc * 32 + gid;
-#pragma unroll
-        for (int k4 = 0; k4 < KC / 4; k4++) {
-            double rf[4], cf[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) rf[i] = a[(k4 * 4 + tig) * LDA_S + i * 8];
-#pragma unroll
-            for (int j = 0; j < 4; j++) cf[j] = b[(k4 * 4 + tig) * LDB_S + j * 8];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) dmma(acc[j][i], cf[j], rf[i]);
-        }
-    }
-
-    // epilogue: thread owns rows (2*tig, 2*tig+1) of column gid in each 8x8 fragment
-    double* cbase = Cg + (int64_t)(wc * 32 + gid) * ldc + wr * 32 + 2 * tig;
     const double alpha = g.alpha, beta = g.beta;
-    if (beta != 0.0) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double2 old[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                old[i] = *reinterpret_cast<const double2*>(cbase + (int64_t)j * 8 * ldc + i * 8);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                double2 o;
-                o.x = fma(alpha, acc[j][i][0], beta * old[i].x);
-                o.y = fma(alpha, acc[j][i][1], beta * old[i].y);
-                *reinterpret_cast<double2*>(cbase + (int64_t)j * 8 * ldc + i * 8) = o;
-            }
-        }
-    } else {
+    int64_t q = 0;  // global chunk counter of this CTA
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        double acc[4][4][2];
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                double2 o = make_double2(alpha * acc[j][i][0], alpha * acc[j][i][1]);
-                *reinterpret_cast<double2*>(cbase + (int64_t)j * 8 * ldc + i * 8) = o;
+            for (int i = 0; i < 4; i++) acc[j][i][0] = acc[j][i][1] = 0.0;
+
+        for (int c = 0; c < nchunks; c++, q++) {
+            const int slot = (int)(q % STAGES);
+            if (warp == 0 && pq < total_q) {
+                // refill the slot of chunk q-1 once all 8 warps have released it
+                if (q > 0) mbar_wait(&empty[(q - 1) % STAGES], (uint32_t)(((q - 1) / STAGES) & 1));
+                issue_next();
             }
+            mbar_wait(&full[slot], (uint32_t)((q / STAGES) & 1));
+            const double* a = sA + slot * KC * LDA_S + wr * 32 + gid;
+            const double* b = sB + slot * KC * LDB_S + wc * 32 + gid;
+#pragma unroll
+            for (int k4 = 0; k4 < KC / 4; k4++) {
+                double rf[4], cf[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) rf[i] = a[(k4 * 4 + tig) * LDA_S + i * 8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) cf[j] = b[(k4 * 4 + tig) * LDB_S + j * 8];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) dmma(acc[j][i], cf[j], rf[i]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+
+        // epilogue: thread owns rows (2*tig, 2*tig+1) of column gid in each 8x8 fragment
+        TilePtrs tp = tile_ptrs(g, tile);
+        double* cbase = tp.C + (int64_t)(wc * 32 + gid) * tp.ldc + wr * 32 + 2 * tig;
+        const int64_t ldc = tp.ldc;
+        if (beta != 0.0) {
+#pragma unroll
+            for (int jh = 0; jh < 2; jh++) {  // 8 x 16-byte loads in flight per thread
+                double2 old[2][4];
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        old[jj][i] = __ldcs(reinterpret_cast<const double2*>(
+                            cbase + (int64_t)(jh * 2 + jj) * 8 * ldc + i * 8));
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int j = jh * 2 + jj;
+                        double2 o;
+                        o.x = fma(alpha, acc[j][i][0], beta * old[jj][i].x);
+                        o.y = fma(alpha, acc[j][i][1], beta * old[jj][i].y);
+                        *reinterpret_cast<double2*>(cbase + (int64_t)j * 8 * ldc + i * 8) = o;
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    double2 o = make_double2(alpha * acc[j][i][0], alpha * acc[j][i][1]);
+                    *reinterpret_cast<double2*>(cbase + (int64_t)j * 8 * ldc + i * 8) = o;
+                }
+        }
     }
 }
 
+int g_num_sms = 0;
 bool g_attr_set = false;
 void ensure_attr() {
     if (!g_attr_set) {
         cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SMEM_BYTES);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         g_attr_set = true;
     }
 }
@@ -238,7 +289,9 @@ void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, 
     g.mtiles = M / BM;
     g.K = K; g.alpha = alpha; g.beta = beta;
     int64_t tiles = (M / BM) * (Ncols / BN);
-    gemm_nt_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, s>>>(g);
+    g.total_tiles = tiles;
+    int64_t grid = tiles < 2 * g_num_sms ? tiles : 2 * g_num_sms;
+    gemm_nt_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g);
     g_launch_count++;
 }
 
@@ -251,8 +304,8 @@ int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int
     return tiles;
 }
 
-void launch_syrk_packed(Packed Apk, int64_t k, const double* P, int64_t jlo, int64_t jhi, int rank,
-                        int world, cudaStream_t s) {
+void launch_syrk_packed(Packed Apk, int64_t k, const double* P, int64_t K, int64_t jlo, int64_t jhi,
+                        int rank, int world, cudaStream_t s) {
     int64_t nblk = Apk.nblk();
     if (jlo < k + 1) jlo = k + 1;
     if (jhi > nblk) jhi = nblk;
@@ -263,9 +316,11 @@ void launch_syrk_packed(Packed Apk, int64_t k, const double* P, int64_t jlo, int
     GemmArgs g{};
     g.mode = 1;
     g.A = P;
-    g.K = NB; g.alpha = -1.0; g.beta = 1.0;
+    g.K = K; g.alpha = -1.0; g.beta = 1.0;
     g.Pk = Apk; g.k = k; g.J0 = J0; g.w = world;
-    gemm_nt_kernel<<<(unsigned)(tiles * 2), THREADS, SMEM_BYTES, s>>>(g);
+    g.total_tiles = tiles * 2;
+    int64_t grid = g.total_tiles < 2 * g_num_sms ? g.total_tiles : 2 * g_num_sms;
+    gemm_nt_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g);
     g_launch_count++;
 }
 

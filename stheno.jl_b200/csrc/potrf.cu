@@ -47,8 +47,19 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
         if (tid > j && tid < NB) s[j * LDS + tid] /= piv;
         __syncthreads();
         if (ri > j) {
-            double lij = s[j * LDS + ri];
-            for (int l = j + 1 + lg; l <= ri; l += PT / NB) s[l * LDS + ri] -= lij * s[j * LDS + l];
+            const double lij = s[j * LDS + ri];
+            int l = j + 1 + lg;
+            for (; l + 12 <= ri; l += 16) {  // 4 independent updates in flight
+                double a0 = s[j * LDS + l], a1 = s[j * LDS + l + 4], a2 = s[j * LDS + l + 8],
+                       a3 = s[j * LDS + l + 12];
+                double c0 = s[l * LDS + ri], c1 = s[(l + 4) * LDS + ri], c2 = s[(l + 8) * LDS + ri],
+                       c3 = s[(l + 12) * LDS + ri];
+                s[l * LDS + ri] = c0 - lij * a0;
+                s[(l + 4) * LDS + ri] = c1 - lij * a1;
+                s[(l + 8) * LDS + ri] = c2 - lij * a2;
+                s[(l + 12) * LDS + ri] = c3 - lij * a3;
+            }
+            for (; l <= ri; l += 4) s[l * LDS + ri] -= lij * s[j * LDS + l];
         }
         __syncthreads();
     }
@@ -84,7 +95,16 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
         double xjj = 1.0 / col[j];
         double acc = 0.0;
         if (row > j) {
-            for (int p = j + 1 + part; p <= row; p += 4) acc += s[p * LDS + row] * col[p];
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            int p = j + 1 + part;
+            for (; p + 12 <= row; p += 16) {
+                b0 = fma(s[p * LDS + row], col[p], b0);
+                b1 = fma(s[(p + 4) * LDS + row], col[p + 4], b1);
+                b2 = fma(s[(p + 8) * LDS + row], col[p + 8], b2);
+                b3 = fma(s[(p + 12) * LDS + row], col[p + 12], b3);
+            }
+            for (; p <= row; p += 4) b0 = fma(s[p * LDS + row], col[p], b0);
+            acc = (b0 + b1) + (b2 + b3);
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);

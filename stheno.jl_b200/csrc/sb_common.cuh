@@ -108,8 +108,9 @@ void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, 
                     cudaStream_t s);
 // trailing update of the packed matrix with panel k held in P (rows from k*NB, ld = ld(k)):
 //   A[I,J] -= P_I * P_J^T   for k < J <= I < nblk   restricted to block columns J with
-//   (J % world) == rank when world > 1, and J in [jlo, jhi)
-void launch_syrk_packed(Packed A, int64_t k, const double* P, int64_t jlo, int64_t jhi,
+//   (J % world) == rank when world > 1, and J in [jlo, jhi).  P has K columns (NB, or 2*NB for
+//   the two-level panel) and leading dimension Np - (k+1)*NB; its row 0 is block row k+1.
+void launch_syrk_packed(Packed A, int64_t k, const double* P, int64_t K, int64_t jlo, int64_t jhi,
                         int rank, int world, cudaStream_t s);
 int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int rank, int world);
 

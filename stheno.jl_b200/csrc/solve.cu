@@ -31,9 +31,12 @@ trsv_diag_kernel(const double* __restrict__ invLk, double* __restrict__ bk, int6
 }
 
 // rows below block k:  b[r] -= sum_c L[r, k*NB + c] * x_k[c]
+// CTA = 64 rows x 4 column groups of 32 columns: 1024 CTAs at m = 64K rows, 16 loads in flight
+// per thread, so the sweep streams L at HBM speed instead of being latency-bound.
 __global__ void __launch_bounds__(256)
 gemv_below_kernel(Packed L, int64_t k, double* __restrict__ b, int S) {
     __shared__ double xs[MAXS][NB];
+    __shared__ double red[3][MAXS][64];
     const int64_t Np = L.Np;
     for (int idx = threadIdx.x; idx < S * NB; idx += 256) {
         int s = idx / NB, c = idx % NB;
@@ -41,43 +44,57 @@ gemv_below_kernel(Packed L, int64_t k, double* __restrict__ b, int S) {
     }
     __syncthreads();
     const int64_t ld = L.ld(k);
-    const int64_t m = ld - NB;
-    int64_t lr = (int64_t)blockIdx.x * 256 + threadIdx.x;  // local row below the diag block
-    if (lr >= m) return;
-    const double* p = L.blk(k + 1, k) + lr;
+    const int rl = threadIdx.x & 63, cg = threadIdx.x >> 6;
+    const int64_t lr = (int64_t)blockIdx.x * 64 + rl;  // m is a multiple of 128
+    const double* p = L.blk(k + 1, k) + lr + (int64_t)(cg * 32) * ld;
     double acc[MAXS];
 #pragma unroll
     for (int s = 0; s < MAXS; s++) acc[s] = 0.0;
-#pragma unroll 8
-    for (int c = 0; c < NB; c++) {
+#pragma unroll 16
+    for (int c = 0; c < 32; c++) {
         double l = p[(int64_t)c * ld];
 #pragma unroll
         for (int s = 0; s < MAXS; s++)
-            if (s < S) acc[s] = fma(l, xs[s][c], acc[s]);
+            if (s < S) acc[s] = fma(l, xs[s][cg * 32 + c], acc[s]);
     }
-    int64_t r = (k + 1) * NB + lr;
+    if (cg > 0) {
 #pragma unroll
-    for (int s = 0; s < MAXS; s++)
-        if (s < S) b[(int64_t)s * Np + r] -= acc[s];
+        for (int s = 0; s < MAXS; s++)
+            if (s < S) red[cg - 1][s][rl] = acc[s];
+    }
+    __syncthreads();
+    if (cg == 0) {
+        int64_t r = (k + 1) * NB + lr;
+#pragma unroll
+        for (int s = 0; s < MAXS; s++)
+            if (s < S) b[(int64_t)s * Np + r] -= acc[s] + red[0][s][rl] + red[1][s][rl] + red[2][s][rl];
+    }
 }
 
 // b_k[c] -= sum_{r below} L[r, k*NB + c] * x[r]   (transposed product, atomics across CTAs)
-constexpr int GT_ROWS = 2048;
+// CTA = 256 rows; each lane keeps its 8 x-values in registers, each warp owns 16 columns.
+constexpr int GT_ROWS = 256;
 __global__ void __launch_bounds__(256)
 gemvT_below_kernel(Packed L, int64_t k, double* __restrict__ b, int S) {
     const int64_t Np = L.Np;
     const int64_t ld = L.ld(k);
-    const int64_t m = ld - NB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t r0 = (int64_t)blockIdx.x * GT_ROWS;
-    int64_t r1 = r0 + GT_ROWS < m ? r0 + GT_ROWS : m;
-    const double* base = L.blk(k + 1, k);
+    const int64_t r0 = (int64_t)blockIdx.x * GT_ROWS;  // m is a multiple of 128; GT_ROWS | 256
+    const int64_t m = ld - NB;
+    const double* base = L.blk(k + 1, k) + r0 + lane;
     for (int s = 0; s < S; s++) {
-        const double* x = b + (int64_t)s * Np + (k + 1) * NB;
-        for (int c = warp; c < NB; c += 8) {
+        const double* x = b + (int64_t)s * Np + (k + 1) * NB + r0 + lane;
+        double xr[GT_ROWS / 32];
+#pragma unroll
+        for (int i = 0; i < GT_ROWS / 32; i++) xr[i] = (r0 + lane + 32 * i < m) ? x[32 * i] : 0.0;
+#pragma unroll 4
+        for (int cc = 0; cc < 16; cc++) {
+            int c = warp * 16 + cc;
             const double* colp = base + (int64_t)c * ld;
             double acc = 0.0;
-            for (int64_t r = r0 + lane; r < r1; r += 32) acc = fma(colp[r], x[r], acc);
+#pragma unroll
+            for (int i = 0; i < GT_ROWS / 32; i++)
+                if (r0 + lane + 32 * i < m) acc = fma(colp[32 * i], xr[i], acc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) atomicAdd(&b[(int64_t)s * Np + k * NB + c], -acc);
@@ -181,7 +198,7 @@ void launch_trsv_diag(const double* invLk, double* bk, int64_t ldb, int S, bool 
 void launch_gemv_below(Packed L, int64_t k, double* b, int S, cudaStream_t s) {
     int64_t m = L.ld(k) - NB;
     if (m <= 0) return;
-    gemv_below_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(L, k, b, S);
+    gemv_below_kernel<<<(unsigned)(m / 64), 256, 0, s>>>(L, k, b, S);
     g_launch_count++;
 }
 

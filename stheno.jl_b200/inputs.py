@@ -65,7 +65,8 @@ class GPPPInput:
 
     def __init__(self, p, x):
         self.p = p
-        self.x = x if isinstance(x, (ColVecs, GPPPInput, BlockData)) else np.asarray(x)
+        # torch CUDA tensors (inputs already resident in HBM) are passed through untouched
+        self.x = x if isinstance(x, (ColVecs, GPPPInput, BlockData)) or hasattr(x, "data_ptr") else np.asarray(x)
 
     def __len__(self):
         return npoints(self.x)

@@ -52,7 +52,7 @@ class sb_timings(C.Structure):
 
 EXPORTS = [
     "sb_abi_version", "sb_last_error", "sb_ctx_create", "sb_nccl_unique_id", "sb_ctx_create_dist",
-    "sb_ctx_destroy", "sb_ctx_timings", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
+    "sb_ctx_destroy", "sb_ctx_timings", "sb_ctx_mark", "sb_ctx_elapsed_ms", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
     "sb_factor_destroy", "sb_factor_logdet", "sb_logpdf", "sb_factor_set_data", "sb_factor_alpha",
     "sb_predict", "sb_predict_cov", "sb_rand", "sb_factor_get_L", "sb_vfe_create", "sb_vfe_predict",
     "sb_vfe_destroy",
@@ -95,6 +95,8 @@ def load():
         "sb_ctx_create_dist": [i32, i32, i32, vp, P(vp)],
         "sb_ctx_destroy": [vp],
         "sb_ctx_timings": [vp, P(sb_timings), i32],
+        "sb_ctx_mark": [vp, i32],
+        "sb_ctx_elapsed_ms": [vp, i32, i32, P(C.c_double)],
         "sb_cov_dense": [vp, P(sb_covspec), vp],
         "sb_cov_diag": [vp, P(sb_covspec), vp],
         "sb_factor_create": [vp, P(sb_covspec), P(sb_noise), P(vp), P(i64)],
@@ -163,6 +165,14 @@ class Context:
         t = sb_timings()
         check(load().sb_ctx_timings(self.h, C.byref(t), 1 if reset else 0))
         return t.asdict()
+
+    def mark(self, slot):
+        check(load().sb_ctx_mark(self.h, slot))
+
+    def elapsed_ms(self, a, b):
+        v = C.c_double()
+        check(load().sb_ctx_elapsed_ms(self.h, a, b, C.byref(v)))
+        return v.value
 
     def close(self):
         if self.h:

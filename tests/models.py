@@ -35,9 +35,10 @@ def rich_model(m):
         f1 = GP(m.SEKernel())
         f2 = GP(1.5, 0.7 * m.Matern32Kernel() + 0.1 * m.WhiteKernel())
         f3 = GP(np.cos, m.with_lengthscale(m.Matern12Kernel(), 2.0) + m.ConstantKernel(0.3))
+        f4 = GP(m.Matern52Kernel())  # only ever seen through the 2-D periodic embedding
         g1 = m.stretch(f1, 0.5) + 2.0 * f2
         g2 = (lambda x: 1.0 + 0.1 * x * x) * m.shift(f1, 0.3) - f3
-        g3 = m.periodic(f1, 0.25) + np.sin + f2
+        g3 = m.periodic(f4, 0.25) + np.sin + f2
         g4 = g1 - g2
-        return dict(f1=f1, f2=f2, f3=f3, g1=g1, g2=g2, g3=g3, g4=g4)
+        return dict(f1=f1, f2=f2, f3=f3, f4=f4, g1=g1, g2=g2, g3=g3, g4=g4)
     return m.gppp(build)
