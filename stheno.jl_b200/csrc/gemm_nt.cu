@@ -26,7 +26,7 @@ constexpr int STAGES = 4;
 constexpr int LDA_S = BM + 4;
 constexpr int LDB_S = BN + 4;
 constexpr int THREADS = 256;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * KC * (LDA_S + LDB_S) * 8 + 2 * STAGES * 8;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * KC * (LDA_S + LDB_S) * 8 + 2 * STAGES * 8 + 8 * 128;
 
 struct GemmArgs {
     int mode;  // 0 plain, 1 packed SYRK
@@ -84,23 +84,6 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
-// tile t of the packed trailing update -> (I, J): columns J_q = J0 + q*w hold R_q = nblk - J_q
-// row blocks (I = J_q .. nblk-1); tiles are enumerated column by column.
-__device__ __forceinline__ void decode_tri(int64_t t, int64_t nblk, int64_t J0, int64_t w,
-                                           int64_t& I, int64_t& J) {
-    double R0 = (double)(nblk - J0);
-    double bq = R0 + 0.5 * (double)w;
-    double disc = bq * bq - 2.0 * (double)w * (double)t;
-    int64_t q = (int64_t)((bq - sqrt(fmax(disc, 0.0))) / (double)w);
-    if (q < 0) q = 0;
-    // S(q) = q*R0 - w*q*(q-1)/2 tiles precede column q
-    auto S = [&](int64_t qq) { return qq * (nblk - J0) - w * (qq * (qq - 1) / 2); };
-    while (q > 0 && S(q) > t) q--;
-    while (S(q + 1) <= t) q++;
-    J = J0 + q * w;
-    I = J + (t - S(q));
-}
-
 struct TilePtrs {
     const double* A;
     const double* B;
@@ -108,39 +91,64 @@ struct TilePtrs {
     int64_t lda, ldb, ldc;
 };
 
-__device__ __forceinline__ TilePtrs tile_ptrs(const GemmArgs& g, int64_t tile) {
-    TilePtrs p;
-    if (g.mode == 0) {
-        int64_t rt = tile % g.mtiles, ct = tile / g.mtiles;
-        p.lda = g.lda; p.ldb = g.ldb; p.ldc = g.ldc;
-        p.A = g.A + rt * BM;
-        p.B = g.B + ct * BN;
-        p.C = g.C + ct * BN * g.ldc + rt * BM;
-    } else {
-        int64_t t = tile >> 1;
-        int h = (int)(tile & 1);
-        int64_t I, J;
-        decode_tri(t, g.Pk.nblk(), g.J0, g.w, I, J);
-        int64_t m = g.Pk.Np - (g.k + 1) * NB;  // panel rows (below the diagonal block of column k)
-        p.lda = p.ldb = m;
-        p.A = g.A + (I - g.k - 1) * NB;
-        p.B = g.A + (J - g.k - 1) * NB + h * BN;
-        p.ldc = g.Pk.ld(J);
-        p.C = g.Pk.blk(I, J) + (int64_t)h * BN * p.ldc;
+// Walks the tiles blockIdx.x, +gridDim.x, ... of one launch.  Packed SYRK tiles are enumerated
+// block column by block column (columns J0, J0+w, ... ; column J holds nblk-J row blocks; two
+// 64-wide half tiles per block), so advancing is a couple of integer compares -- no division,
+// no square root.
+struct TileCursor {
+    int64_t t;     // linear tile index
+    int64_t J;     // packed: current block column
+    int64_t s0;    // packed: linear index of the first (half-)tile of column J
+    __device__ __forceinline__ void init(const GemmArgs& g, int64_t t0) {
+        t = t0;
+        J = g.J0;
+        s0 = 0;
+        if (g.mode == 1) seek(g);
     }
-    return p;
-}
+    __device__ __forceinline__ void seek(const GemmArgs& g) {
+        const int64_t nblk = g.Pk.nblk();
+        while (t - s0 >= 2 * (nblk - J)) {
+            s0 += 2 * (nblk - J);
+            J += g.w;
+        }
+    }
+    __device__ __forceinline__ void advance(const GemmArgs& g, int64_t step) {
+        t += step;
+        if (g.mode == 1 && t < g.total_tiles) seek(g);
+    }
+    __device__ __forceinline__ TilePtrs ptrs(const GemmArgs& g) const {
+        TilePtrs p;
+        if (g.mode == 0) {
+            int64_t rt = t % g.mtiles, ct = t / g.mtiles;
+            p.lda = g.lda; p.ldb = g.ldb; p.ldc = g.ldc;
+            p.A = g.A + rt * BM;
+            p.B = g.B + ct * BN;
+            p.C = g.C + ct * BN * g.ldc + rt * BM;
+        } else {
+            const int64_t loc = t - s0;
+            const int64_t I = J + (loc >> 1);
+            const int h = (int)(loc & 1);
+            const int64_t m = g.Pk.Np - (g.k + 1) * NB;  // panel rows below diagonal block k
+            p.lda = p.ldb = m;
+            p.A = g.A + (I - g.k - 1) * NB;
+            p.B = g.A + (J - g.k - 1) * NB + h * BN;
+            p.ldc = g.Pk.ld(J);
+            p.C = g.Pk.blk(I, J) + (int64_t)h * BN * p.ldc;
+        }
+        return p;
+    }
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // Persistent CTAs (2 per SM): each walks tiles blockIdx.x, +gridDim.x, ...  The operand ring is
-// addressed by a global chunk counter that runs ACROSS tiles, so the TMA engine is already
-// filling the next tile's first k-slabs while the warps are still in the current tile's
-// epilogue.  No CTA-wide barrier in the steady state: full[] (TMA -> warps, tx-count) and empty[]
-// (8 warps -> producer lane) mbarriers only.
-__global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmArgs g) {
+// addressed by a chunk counter that runs ACROSS tiles, so the TMA engine is already filling the
+// next tile's first k-slabs while the warps are still in the current tile's epilogue.  No
+// CTA-wide barrier in the steady state: full[] (TMA -> warps, tx-count) and empty[] (8 warps ->
+// producer lane) mbarriers only.
+__global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_constant__ GemmArgs g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
     double* sB = sA + STAGES * KC * LDA_S;
@@ -150,13 +158,11 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmArgs g) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
     const int nchunks = (int)(g.K / KC);
-    const int64_t ntiles_cta = (g.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const int64_t total_q = ntiles_cta * nchunks;
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], THREADS / 32);  // one arrive.expect_tx per issuing warp
             mbar_init(&empty[s], THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,59 +170,86 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmArgs g) {
     }
     __syncthreads();
 
-    // ---- producer state (warp 0 only) -------------------------------------------------------
-    int64_t pq = 0;          // next global chunk to issue
-    int pc = 0;              // its k-chunk inside the tile
-    TilePtrs pp = tile_ptrs(g, blockIdx.x);
-    int64_t ptile = blockIdx.x;
-    auto issue_next = [&]() {  // all lanes of warp 0
-        int slot = (int)(pq % STAGES);
-        if (lane == 0) mbar_expect_tx(&full[slot], (BM + BN) * KC * 8);
-        __syncwarp();
-        int kk = lane & 15;
-        int64_t kg = (int64_t)pc * KC + kk;
-        if (lane < 16)
-            bulk_g2s(sA + (slot * KC + kk) * LDA_S, pp.A + kg * pp.lda, BM * 8, &full[slot]);
-        else
-            bulk_g2s(sB + (slot * KC + kk) * LDB_S, pp.B + kg * pp.ldb, BN * 8, &full[slot]);
-        pq++;
-        if (++pc == nchunks) {
-            pc = 0;
-            ptile += gridDim.x;
-            if (ptile < g.total_tiles) pp = tile_ptrs(g, ptile);
-        }
+    // ---- distributed producer: lane 0 of EVERY warp issues its 4 of the 32 bulk copies of a
+    // k-slab (a bulk copy costs its issuing thread ~30 ns -- tools/mb_bulk.cu -- so one lane
+    // issuing all 32 sat on warp 0's critical path).  Lane 0 of warp 0 additionally arms the
+    // slab's mbarrier with the byte count.  Each warp tracks the producer cursor redundantly
+    // (identical values in all warps), in registers of lane 0 only via a small shared struct.
+    struct ProducerState {
+        TileCursor cur;
+        TilePtrs pp;
+        int pc, pslot;
+        uint32_t pphase;  // parity to wait for on empty[pslot] before refilling it
+        int pfirst;       // first pass over the ring: slots are fresh, no wait
+        int pdone;
     };
-    if (warp == 0) {
-        for (int c = 0; c < STAGES - 1 && pq < total_q; c++) issue_next();
+    ProducerState* ps = reinterpret_cast<ProducerState*>(empty + STAGES) + warp;
+    auto issue_next = [&]() {  // lane 0 of each warp
+        ProducerState st = *ps;
+        if (!st.pfirst) mbar_wait(&empty[st.pslot], st.pphase);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[st.pslot], (BM + BN) * 2 * 8);  // this warp's 2 + 2 columns
+        const double* srcA = st.pp.A + ((int64_t)st.pc * KC + warp * 2) * st.pp.lda;
+        const double* srcB = st.pp.B + ((int64_t)st.pc * KC + warp * 2) * st.pp.ldb;
+        double* dA = sA + (st.pslot * KC + warp * 2) * LDA_S;
+        double* dB = sB + (st.pslot * KC + warp * 2) * LDB_S;
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            bulk_g2s(dA + kk * LDA_S, srcA + kk * st.pp.lda, BM * 8, &full[st.pslot]);
+            bulk_g2s(dB + kk * LDB_S, srcB + kk * st.pp.ldb, BN * 8, &full[st.pslot]);
+        }
+        if (++st.pslot == STAGES) {
+            st.pslot = 0;
+            if (st.pfirst) st.pfirst = 0; else st.pphase ^= 1;
+        }
+        if (++st.pc == nchunks) {
+            st.pc = 0;
+            st.cur.advance(g, gridDim.x);
+            st.pdone = st.cur.t >= g.total_tiles;
+            if (!st.pdone) st.pp = st.cur.ptrs(g);
+        }
+        *ps = st;
+    };
+    const bool producer = (lane == 0);
+    if (producer) {
+        ProducerState st;
+        st.cur.init(g, blockIdx.x);
+        st.pc = 0; st.pslot = 0; st.pphase = 0; st.pfirst = 1;
+        st.pdone = st.cur.t >= g.total_tiles;
+        if (!st.pdone) st.pp = st.cur.ptrs(g);
+        *ps = st;
+        for (int c = 0; c < STAGES - 1 && !ps->pdone; c++) issue_next();
     }
 
     const int wr = warp & 3, wc = warp >> 2;  // 4 warps along rows, 2 along cols; 32x32 each
     const double alpha = g.alpha, beta = g.beta;
-    int64_t q = 0;  // global chunk counter of this CTA
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+    const double* a_base = sA + wr * 32 + gid + tig * LDA_S;
+    const double* b_base = sB + wc * 32 + gid + tig * LDB_S;
+    int slot = 0;
+    uint32_t phase = 0;
+    TileCursor cur;
+    cur.init(g, blockIdx.x);
+    for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x)) {
         double acc[4][4][2];
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) acc[j][i][0] = acc[j][i][1] = 0.0;
 
-        for (int c = 0; c < nchunks; c++, q++) {
-            const int slot = (int)(q % STAGES);
-            if (warp == 0 && pq < total_q) {
-                // refill the slot of chunk q-1 once all 8 warps have released it
-                if (q > 0) mbar_wait(&empty[(q - 1) % STAGES], (uint32_t)(((q - 1) / STAGES) & 1));
-                issue_next();
-            }
-            mbar_wait(&full[slot], (uint32_t)((q / STAGES) & 1));
-            const double* a = sA + slot * KC * LDA_S + wr * 32 + gid;
-            const double* b = sB + slot * KC * LDB_S + wc * 32 + gid;
+        for (int c = 0; c < nchunks; c++) {
+            // keep the ring STAGES-1 slabs ahead: refill the slot released by the previous chunk
+            if (producer && !ps->pdone) issue_next();
+            __syncwarp();
+            mbar_wait(&full[slot], phase);
+            const double* a = a_base + slot * KC * LDA_S;
+            const double* b = b_base + slot * KC * LDB_S;
 #pragma unroll
             for (int k4 = 0; k4 < KC / 4; k4++) {
                 double rf[4], cf[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) rf[i] = a[(k4 * 4 + tig) * LDA_S + i * 8];
+                for (int i = 0; i < 4; i++) rf[i] = a[k4 * 4 * LDA_S + i * 8];
 #pragma unroll
-                for (int j = 0; j < 4; j++) cf[j] = b[(k4 * 4 + tig) * LDB_S + j * 8];
+                for (int j = 0; j < 4; j++) cf[j] = b[k4 * 4 * LDB_S + j * 8];
 #pragma unroll
                 for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -224,10 +257,11 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmArgs g) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
+            if (++slot == STAGES) { slot = 0; phase ^= 1; }
         }
 
         // epilogue: thread owns rows (2*tig, 2*tig+1) of column gid in each 8x8 fragment
-        TilePtrs tp = tile_ptrs(g, tile);
+        TilePtrs tp = cur.ptrs(g);
         double* cbase = tp.C + (int64_t)(wc * 32 + gid) * tp.ldc + wr * 32 + 2 * tig;
         const int64_t ldc = tp.ldc;
         if (beta != 0.0) {

@@ -158,3 +158,19 @@ def test_not_positive_definite(sb):
     with pytest.raises(sb.PosDefException) as ei:
         sb.logpdf(fs(sb.GPPPInput("f", x), 0.0), np.zeros(400))
     assert 1 <= ei.value.info <= 400
+
+
+def test_factorisation_is_race_free_and_deterministic(sb):
+    """Stress the TMA ring of the DMMA kernel: repeated factorisations of the same matrix must be
+    bit-identical (a missing generic->async proxy fence once produced rare stale-operand reads)."""
+    rng = np.random.default_rng(99)
+    n = 2048
+    x = rng.uniform(0, n / 32, n)
+    y = rng.standard_normal(n)
+    f = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel())))
+    ref = None
+    for _ in range(25):
+        lp = sb.logpdf(f(sb.GPPPInput("f", x), 0.1), y)
+        if ref is None:
+            ref = lp
+        assert lp == ref
