@@ -213,16 +213,26 @@ def gpu_main(args):
     noise.sigma2, noise.diag = SIGMA2, None
     lp_out = (C.c_double * 1)()
 
+    call_s = {"factor": 0.0, "logpdf": 0.0, "set_data": 0.0, "predict": 0.0, "destroy": 0.0}
+
     def device_step():
         h = C.c_void_p()
         info = C.c_int64(0)
+        t0 = time.perf_counter()
         sblib.check(lib.sb_factor_create(ctx.h, C.byref(spec_k), C.byref(noise), C.byref(h), C.byref(info)), info)
+        t1 = time.perf_counter()
         try:
             sblib.check(lib.sb_logpdf(ctx.h, h, yd.data_ptr(), 1, lp_out))           # zero-mean: delta = y
+            t2 = time.perf_counter()
             sblib.check(lib.sb_factor_set_data(ctx.h, h, yd.data_ptr()))
+            t3 = time.perf_counter()
             sblib.check(lib.sb_predict(ctx.h, h, C.byref(spec_c), C.byref(spec_d), mean_d.data_ptr(), var_d.data_ptr()))
+            t4 = time.perf_counter()
         finally:
             lib.sb_factor_destroy(h)
+        t5 = time.perf_counter()
+        for k, v in zip(call_s, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            call_s[k] += v
         return lp_out[0]
 
     def barrier():
@@ -233,6 +243,8 @@ def gpu_main(args):
 
     for _ in range(args.warmup):
         device_step()
+    for k in call_s:
+        call_s[k] = 0.0
     barrier()
     ctx.timings(reset=True)
     sampler = ClockSampler(local)
@@ -329,7 +341,8 @@ def gpu_main(args):
         "e2e": {"value": n / e2e_s, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3},
         "gpu_launches": tm["kernel_launches"], "roofline": roof, "roofline_assemble": roof_asm,
-        "phases_ms": phases, "logpdf": lp, "clocks": clocks,
+        "phases_ms": phases, "host_call_ms": {k: v * 1e3 / args.steps for k, v in call_s.items()},
+        "logpdf": lp, "clocks": clocks,
     }
     if cb:
         out["cpu_baseline"] = cb

@@ -38,6 +38,7 @@ typedef ncclResult_t (*CommInitRank_t)(ncclComm_t*, int, ncclUniqueId, int);
 typedef ncclResult_t (*CommDestroy_t)(ncclComm_t);
 typedef ncclResult_t (*Broadcast_t)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
 typedef ncclResult_t (*AllReduce_t)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*AllGather_t)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
 typedef ncclResult_t (*Group_t)(void);
 typedef const char* (*ErrStr_t)(ncclResult_t);
 static GetUniqueId_t GetUniqueId;
@@ -45,6 +46,7 @@ static CommInitRank_t CommInitRank;
 static CommDestroy_t CommDestroy;
 static Broadcast_t Broadcast;
 static AllReduce_t AllReduce;
+static AllGather_t AllGather;
 static Group_t GroupStart, GroupEnd;
 static ErrStr_t GetErrorString;
 static bool loaded = false;
@@ -57,7 +59,7 @@ static bool load() {
         return false;
     }
 #define SB_SYM(name) name = (name##_t)dlsym(h, "nccl" #name); if (!name) { sb::set_error("missing NCCL symbol nccl" #name); return false; }
-    SB_SYM(GetUniqueId) SB_SYM(CommInitRank) SB_SYM(CommDestroy) SB_SYM(Broadcast) SB_SYM(AllReduce)
+    SB_SYM(GetUniqueId) SB_SYM(CommInitRank) SB_SYM(CommDestroy) SB_SYM(Broadcast) SB_SYM(AllReduce) SB_SYM(AllGather)
     GroupStart = (Group_t)dlsym(h, "ncclGroupStart");
     GroupEnd = (Group_t)dlsym(h, "ncclGroupEnd");
     GetErrorString = (ErrStr_t)dlsym(h, "ncclGetErrorString");
@@ -86,6 +88,43 @@ struct sb_ctx {
     sb_timings tm{};
     bool fine_timing = true;
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // caching device allocator: the factor (17 GB at N=65536) and the posterior workspace are
+    // re-used across calls instead of paying cudaMalloc/cudaFree (both device-synchronising)
+    struct PoolBlock { size_t bytes; void* p; };
+    std::vector<PoolBlock> pool_free_list;
+    size_t pool_cached_bytes = 0;
+    cudaError_t pool_alloc(void** out, size_t bytes) {
+        if (bytes == 0) bytes = 8;
+        int best = -1;
+        for (int i = 0; i < (int)pool_free_list.size(); i++) {
+            size_t b = pool_free_list[i].bytes;
+            if (b >= bytes && b <= bytes + bytes / 4 + 4096 && (best < 0 || b < pool_free_list[best].bytes)) best = i;
+        }
+        if (best >= 0) {
+            *out = pool_free_list[best].p;
+            pool_cached_bytes -= pool_free_list[best].bytes;
+            pool_free_list.erase(pool_free_list.begin() + best);
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaErrorMemoryAllocation && !pool_free_list.empty()) {
+            cudaGetLastError();
+            pool_trim();
+            e = cudaMalloc(out, bytes);
+        }
+        return e;
+    }
+    void pool_release(void* p, size_t bytes) {
+        if (!p) return;
+        if (bytes == 0) bytes = 8;
+        pool_free_list.push_back({bytes, p});
+        pool_cached_bytes += bytes;
+    }
+    void pool_trim() {
+        for (auto& b : pool_free_list) cudaFree(b.p);
+        pool_free_list.clear();
+        pool_cached_bytes = 0;
+    }
     std::vector<cudaEvent_t> ev;
     size_t ev_used = 0;
     cudaEvent_t next_event() {
@@ -109,6 +148,7 @@ struct sb_factor {
     double* alpha = nullptr;  // Np
     bool has_alpha = false;
     double logdet = 0.0;
+    size_t bytes_L = 0, bytes_invL = 0, bytes_ld = 0, bytes_panel = 0, bytes_alpha = 0;
 };
 
 namespace {
@@ -132,11 +172,17 @@ struct PhaseTimer {  // accumulates the stream time between start() and stop() i
 
 struct DevBuf {
     void* p = nullptr;
+    size_t bytes = 0;
+    sb_ctx* ctx = nullptr;
+    DevBuf() {}
+    explicit DevBuf(sb_ctx* c) : ctx(c) {}
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (!p) return;
+        if (ctx) ctx->pool_release(p, bytes); else cudaFree(p);
     }
-    int32_t alloc(size_t bytes) {
-        SB_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+    int32_t alloc(size_t nbytes) {
+        bytes = nbytes ? nbytes : 8;
+        if (ctx) SB_CUDA(ctx->pool_alloc(&p, bytes)); else SB_CUDA(cudaMalloc(&p, bytes));
         return SB_OK;
     }
     double* d() { return reinterpret_cast<double*>(p); }
@@ -145,6 +191,7 @@ struct DevBuf {
 // uploaded covariance plan
 struct DevSpec {
     DevBuf pool;
+    explicit DevSpec(sb_ctx* c) : pool(c) {}
     std::vector<double*> arr;
     std::vector<BlockDev> blocks;
     int64_t nrows = 0, ncols = 0;
@@ -217,6 +264,33 @@ struct DevSpec {
         return SB_OK;
     }
 };
+
+// keep only rows [lo, hi) of every block (and, for paired/diag specs, the same range of columns);
+// rows are re-based to lo.  Used to shard the posterior's test points across ranks.
+void clip_rows(DevSpec& ds, int64_t lo, int64_t hi, bool diag) {
+    std::vector<BlockDev> out;
+    for (BlockDev b : ds.blocks) {
+        int64_t r0 = b.row0 > lo ? b.row0 : lo;
+        int64_t r1 = b.row0 + b.nrows < hi ? b.row0 + b.nrows : hi;
+        if (r1 <= r0) continue;
+        int64_t off = r0 - b.row0;
+        for (int t = 0; t < b.nterms; t++) {
+            b.t[t].zl += off * b.t[t].dim;
+            if (b.t[t].sl) b.t[t].sl += off;
+            if (diag) {
+                b.t[t].zr += off * b.t[t].dim;
+                if (b.t[t].sr) b.t[t].sr += off;
+            }
+        }
+        b.row0 = r0 - lo;
+        b.nrows = r1 - r0;
+        if (diag) { b.col0 = b.row0; b.ncols = b.nrows; }
+        out.push_back(b);
+    }
+    ds.blocks.swap(out);
+    ds.nrows = hi - lo;
+    if (diag) ds.ncols = hi - lo;
+}
 
 void begin_call(sb_ctx* c) {
     cudaSetDevice(c->device);
@@ -462,6 +536,7 @@ int32_t sb_ctx_destroy(sb_ctx* c) {
     if (!c) return SB_OK;
     cudaSetDevice(c->device);
     if (c->comm) nccl_dl::CommDestroy(c->comm);
+    c->pool_trim();
     for (auto e : c->ev) cudaEventDestroy(e);
     for (auto e : c->marks) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -498,9 +573,9 @@ int32_t sb_cov_dense(sb_ctx* c, const sb_covspec* spec, void* K_out) {
     SB_CHECK(c && spec && K_out, "null argument");
     begin_call(c);
     int64_t before = g_launch_count;
-    DevSpec ds;
+    DevSpec ds(c);
     SB_TRY(ds.build(spec, c->stream, false));
-    DevBuf K;
+    DevBuf K(c);
     size_t bytes = (size_t)ds.nrows * ds.ncols * sizeof(double);
     SB_TRY(K.alloc(bytes));
     SB_CUDA(cudaMemsetAsync(K.p, 0, bytes, c->stream));
@@ -518,9 +593,9 @@ int32_t sb_cov_diag(sb_ctx* c, const sb_covspec* spec, void* out) {
     SB_CHECK(c && spec && out, "null argument");
     begin_call(c);
     int64_t before = g_launch_count;
-    DevSpec ds;
+    DevSpec ds(c);
     SB_TRY(ds.build(spec, c->stream, true));
-    DevBuf v;
+    DevBuf v(c);
     SB_TRY(v.alloc(ds.nrows * sizeof(double)));
     SB_CUDA(cudaMemsetAsync(v.p, 0, ds.nrows * sizeof(double), c->stream));
     SB_TRY(assemble_diag(c, ds, v.d()));
@@ -533,12 +608,13 @@ int32_t sb_cov_diag(sb_ctx* c, const sb_covspec* spec, void* out) {
 int32_t sb_factor_destroy(sb_factor* f) {
     if (!f) return SB_OK;
     cudaSetDevice(f->ctx->device);
-    cudaFree(f->L.base);
-    cudaFree(f->invL);
-    cudaFree(f->logdet_blk);
-    cudaFree(f->info_dev);
-    cudaFree(f->panel);
-    cudaFree(f->alpha);
+    sb_ctx* c = f->ctx;
+    c->pool_release(f->L.base, f->bytes_L);
+    c->pool_release(f->invL, f->bytes_invL);
+    c->pool_release(f->logdet_blk, f->bytes_ld);
+    c->pool_release(f->info_dev, 8);
+    c->pool_release(f->panel, f->bytes_panel);
+    c->pool_release(f->alpha, f->bytes_alpha);
     delete f;
     return SB_OK;
 }
@@ -555,7 +631,7 @@ int32_t sb_factor_create(sb_ctx* c, const sb_covspec* spec, const sb_noise* nois
     cudaEvent_t t0 = c->next_event(), t1 = c->next_event();
     cudaEventRecord(t0, c->stream);
 
-    DevSpec ds;
+    DevSpec ds(c);
     SB_TRY(ds.build(spec, c->stream, false));
     sb_factor* f = new sb_factor();
     f->ctx = c;
@@ -572,16 +648,21 @@ int32_t sb_factor_create(sb_ctx* c, const sb_covspec* spec, const sb_noise* nois
         cudaError_t _e = (call);                                               \
         if (_e != cudaSuccess) return fail(sb::cuda_fail(_e, #call, __FILE__, __LINE__)); \
     } while (0)
-    SB_CUDA_F(cudaMalloc(&f->L.base, (size_t)f->L.total() * sizeof(double)));
-    SB_CUDA_F(cudaMalloc(&f->invL, (size_t)nblk * NB * NB * sizeof(double)));
-    SB_CUDA_F(cudaMalloc(&f->logdet_blk, (size_t)nblk * sizeof(double)));
-    SB_CUDA_F(cudaMalloc(&f->info_dev, sizeof(long long)));
-    SB_CUDA_F(cudaMalloc(&f->panel, (size_t)2 * f->Np * NB * sizeof(double)));  // Np x 256 panel pair
-    SB_CUDA_F(cudaMalloc(&f->alpha, (size_t)f->Np * sizeof(double)));
+    f->bytes_L = (size_t)f->L.total() * sizeof(double);
+    f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
+    f->bytes_ld = (size_t)nblk * sizeof(double);
+    f->bytes_panel = (size_t)2 * f->Np * NB * sizeof(double);  // Np x 256 panel pair
+    f->bytes_alpha = (size_t)f->Np * sizeof(double);
+    SB_CUDA_F(c->pool_alloc((void**)&f->L.base, f->bytes_L));
+    SB_CUDA_F(c->pool_alloc((void**)&f->invL, f->bytes_invL));
+    SB_CUDA_F(c->pool_alloc((void**)&f->logdet_blk, f->bytes_ld));
+    SB_CUDA_F(c->pool_alloc((void**)&f->info_dev, 8));
+    SB_CUDA_F(c->pool_alloc((void**)&f->panel, f->bytes_panel));
+    SB_CUDA_F(c->pool_alloc((void**)&f->alpha, f->bytes_alpha));
     SB_CUDA_F(cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream));
     SB_CUDA_F(cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream));
 
-    DevBuf nd;
+    DevBuf nd(c);
     const double* noise_diag = nullptr;
     double sigma2 = 0.0;
     if (noise) {
@@ -644,7 +725,7 @@ int32_t sb_logpdf(sb_ctx* c, sb_factor* f, const void* delta, int32_t S, double*
     SB_CHECK(c && f && delta && out && S >= 1, "bad argument");
     begin_call(c);
     int64_t before = g_launch_count;
-    DevBuf b, q;
+    DevBuf b(c), q(c);
     SB_TRY(b.alloc((size_t)f->Np * S * sizeof(double)));
     SB_TRY(q.alloc(S * sizeof(double)));
     SB_TRY(upload_padded(c, delta, f->N, f->Np, S, b.d()));
@@ -695,29 +776,51 @@ static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
     begin_call(c);
     int64_t before = g_launch_count;
     SB_CHECK(cross->ncols == f->N, "cross spec must be N* x N");
-    const int64_t Ns = cross->nrows, Nsp = round_up(Ns, NB), Np = f->Np;
+    const int64_t Ns_all = cross->nrows;
+    if (Ns_all == 0) return SB_OK;
+    // multi-GPU: every rank holds the complete factor, so the test points are sharded by rows
+    // (contiguous chunks) with no communication until the final all-gather of mean / var.
+    const bool shard = c->world > 1 && !full_cov;
+    const int64_t chunk = shard ? (Ns_all + c->world - 1) / c->world : Ns_all;
+    const int64_t lo = shard ? (c->rank * chunk < Ns_all ? c->rank * chunk : Ns_all) : 0;
+    const int64_t hi = shard ? (lo + chunk < Ns_all ? lo + chunk : Ns_all) : Ns_all;
+    const int64_t Ns = hi - lo, Nsp = round_up(Ns > 0 ? Ns : 1, NB), Np = f->Np;
     const int64_t nblk = f->L.nblk();
-    if (Ns == 0) return SB_OK;
     const bool need_var = var_out != nullptr || full_cov;
     SB_CHECK(!mean_out || f->has_alpha, "posterior mean requested before sb_factor_set_data");
     cudaEvent_t t0 = c->next_event(), t1 = c->next_event();
     cudaEventRecord(t0, c->stream);
 
-    DevSpec dc, dp;
+    DevSpec dc(c), dp(c);
     SB_TRY(dc.build(cross, c->stream, false));
     if (need_var) {
         SB_CHECK(prior != nullptr, "prior spec required for var/cov");
-        SB_CHECK(prior->nrows == Ns, "prior spec size mismatch");
+        SB_CHECK(prior->nrows == Ns_all, "prior spec size mismatch");
         SB_TRY(dp.build(prior, c->stream, !full_cov));
     }
-    DevBuf W, Xk, mean, acc, pd;
+    if (shard) {
+        clip_rows(dc, lo, hi, false);
+        if (need_var) clip_rows(dp, lo, hi, true);
+    }
+    DevBuf gath(c);  // [2][world][chunk] gather buffer (mean, var) when sharded
+    if (shard) SB_TRY(gath.alloc((size_t)2 * (c->world + 1) * chunk * sizeof(double)));
+    double* g_send_m = shard ? gath.d() : nullptr;                       // chunk
+    double* g_send_v = shard ? gath.d() + chunk : nullptr;               // chunk
+    double* g_recv_m = shard ? gath.d() + 2 * chunk : nullptr;           // world*chunk
+    double* g_recv_v = shard ? gath.d() + 2 * chunk + (size_t)c->world * chunk : nullptr;
+    if (shard) SB_CUDA(cudaMemsetAsync(gath.p, 0, (size_t)2 * (c->world + 1) * chunk * sizeof(double), c->stream));
+    DevBuf W(c), Xk(c), mean(c), acc(c), pd(c);
     SB_TRY(W.alloc((size_t)Nsp * Np * sizeof(double)));
     SB_CUDA(cudaMemsetAsync(W.p, 0, (size_t)Nsp * Np * sizeof(double), c->stream));
     SB_TRY(assemble_dense(c, dc, W.d(), Nsp));
     if (mean_out) {
         SB_TRY(mean.alloc(Nsp * sizeof(double)));
         launch_gemv_n(W.d(), Nsp, Nsp, Np, f->alpha, mean.d(), c->stream);
-        SB_CUDA(cudaMemcpyAsync(mean_out, mean.p, Ns * sizeof(double), cudaMemcpyDefault, c->stream));
+        if (shard) {
+            if (Ns > 0) SB_CUDA(cudaMemcpyAsync(g_send_m, mean.p, Ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            SB_CUDA(cudaMemcpyAsync(mean_out, mean.p, Ns * sizeof(double), cudaMemcpyDefault, c->stream));
+        }
     }
     if (need_var) {
         SB_TRY(Xk.alloc((size_t)Nsp * NB * sizeof(double)));
@@ -744,11 +847,14 @@ static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
             SB_CUDA(cudaMemsetAsync(pd.p, 0, Nsp * sizeof(double), c->stream));
             SB_TRY(assemble_diag(c, dp, pd.d()));
             launch_sub(pd.d(), pd.d(), acc.d(), Ns, c->stream);
-            if (var_out)
+            if (var_out && shard) {
+                if (Ns > 0) SB_CUDA(cudaMemcpyAsync(g_send_v, pd.p, Ns * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            } else if (var_out) {
                 SB_CUDA(cudaMemcpyAsync(var_out, pd.p, Ns * sizeof(double), cudaMemcpyDefault, c->stream));
+            }
         } else {
             // cov = prior_full - V^T V  = prior_full - W W^T   (W now holds V^T, Nsp x Np)
-            DevBuf Cm;
+            DevBuf Cm(c);
             SB_TRY(Cm.alloc((size_t)Nsp * Nsp * sizeof(double)));
             SB_CUDA(cudaMemsetAsync(Cm.p, 0, (size_t)Nsp * Nsp * sizeof(double), c->stream));
             SB_TRY(assemble_dense(c, dp, Cm.d(), Nsp));
@@ -759,6 +865,16 @@ static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
         }
     }
     SB_CUDA(cudaGetLastError());
+    if (shard) {
+        if (mean_out) {
+            SB_NCCL(nccl_dl::AllGather(g_send_m, g_recv_m, (size_t)chunk, ncclDouble, c->comm, c->stream));
+            SB_CUDA(cudaMemcpyAsync(mean_out, g_recv_m, Ns_all * sizeof(double), cudaMemcpyDefault, c->stream));
+        }
+        if (var_out) {
+            SB_NCCL(nccl_dl::AllGather(g_send_v, g_recv_v, (size_t)chunk, ncclDouble, c->comm, c->stream));
+            SB_CUDA(cudaMemcpyAsync(var_out, g_recv_v, Ns_all * sizeof(double), cudaMemcpyDefault, c->stream));
+        }
+    }
     cudaEventRecord(t1, c->stream);
     SB_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -785,7 +901,7 @@ int32_t sb_rand(sb_ctx* c, sb_factor* f, const void* z, int32_t S, void* out) {
     SB_CHECK(c && f && z && out && S >= 1, "bad argument");
     begin_call(c);
     int64_t before = g_launch_count;
-    DevBuf zb, ob;
+    DevBuf zb(c), ob(c);
     SB_TRY(zb.alloc((size_t)f->Np * S * sizeof(double)));
     SB_TRY(ob.alloc((size_t)f->Np * S * sizeof(double)));
     SB_TRY(upload_padded(c, z, f->N, f->Np, S, zb.d()));
@@ -802,7 +918,7 @@ int32_t sb_factor_get_L(sb_ctx* c, sb_factor* f, void* L_out) {
     SB_CHECK(c && f && L_out, "null argument");
     SB_CHECK(f->N <= 65535, "sb_factor_get_L is a debug path (N <= 65535)");
     begin_call(c);
-    DevBuf d;
+    DevBuf d(c);
     SB_TRY(d.alloc((size_t)f->N * f->N * sizeof(double)));
     launch_unpack_lower(f->L, f->N, d.d(), c->stream);
     SB_CUDA(cudaGetLastError());

@@ -34,9 +34,9 @@ class _Factor:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:  # the ctx owns the pool the factor returns its memory to
                 _lib.load().sb_factor_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -335,9 +335,9 @@ class _VfeHandle:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:
                 _lib.load().sb_vfe_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
