@@ -148,6 +148,14 @@ int32_t sb_ctx_timings(sb_ctx* ctx, sb_timings* out, int32_t reset);
 int32_t sb_ctx_mark(sb_ctx* ctx, int32_t slot);
 int32_t sb_ctx_elapsed_ms(sb_ctx* ctx, int32_t slot_a, int32_t slot_b, double* ms);
 
+/* ---- multi-GPU partition helpers (pure host arithmetic; also what the CPU gloo tests check) --
+ * sb_owner_of_block: rank owning block column J (1-D block-cyclic).
+ * sb_owned_trailing_tiles: number of 128x128 trailing tiles (k < J <= I < nblk) rank updates at
+ *   step k.  sb_row_chunk: contiguous [lo, hi) share of ns posterior test points for a rank. */
+int32_t sb_owner_of_block(int64_t J, int32_t world);
+int64_t sb_owned_trailing_tiles(int64_t nblk, int64_t k, int32_t rank, int32_t world);
+int32_t sb_row_chunk(int64_t ns, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+
 /* ---- covariance assembly ---------------------------------------------------------------
  * sb_cov_dense replaces  cov(f::GPPP, x[, x'])  -> Matrix
  *   (gaussian_process_probabilistic_programme.jl:50-64 -> cross.jl:59-86 ->

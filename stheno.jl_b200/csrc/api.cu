@@ -552,6 +552,21 @@ int32_t sb_ctx_timings(sb_ctx* c, sb_timings* out, int32_t reset) {
     return SB_OK;
 }
 
+int32_t sb_owner_of_block(int64_t J, int32_t world) { return world > 0 ? (int32_t)(J % world) : 0; }
+
+int64_t sb_owned_trailing_tiles(int64_t nblk, int64_t k, int32_t rank, int32_t world) {
+    if (world < 1 || rank < 0 || rank >= world) return -1;
+    return syrk_packed_tiles(nblk, k, k + 1, nblk, rank, world);
+}
+
+int32_t sb_row_chunk(int64_t ns, int32_t rank, int32_t world, int64_t* lo, int64_t* hi) {
+    SB_CHECK(lo && hi && world >= 1 && rank >= 0 && rank < world && ns >= 0, "bad argument");
+    int64_t chunk = (ns + world - 1) / world;
+    *lo = rank * chunk < ns ? rank * chunk : ns;
+    *hi = *lo + chunk < ns ? *lo + chunk : ns;
+    return SB_OK;
+}
+
 int32_t sb_ctx_mark(sb_ctx* c, int32_t slot) {
     SB_CHECK(c && slot >= 0 && slot < 8, "bad mark slot");
     cudaSetDevice(c->device);

@@ -52,7 +52,8 @@ class sb_timings(C.Structure):
 
 EXPORTS = [
     "sb_abi_version", "sb_last_error", "sb_ctx_create", "sb_nccl_unique_id", "sb_ctx_create_dist",
-    "sb_ctx_destroy", "sb_ctx_timings", "sb_ctx_mark", "sb_ctx_elapsed_ms", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
+    "sb_ctx_destroy", "sb_ctx_timings", "sb_ctx_mark", "sb_ctx_elapsed_ms", "sb_owner_of_block",
+    "sb_owned_trailing_tiles", "sb_row_chunk", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
     "sb_factor_destroy", "sb_factor_logdet", "sb_logpdf", "sb_factor_set_data", "sb_factor_alpha",
     "sb_predict", "sb_predict_cov", "sb_rand", "sb_factor_get_L", "sb_vfe_create", "sb_vfe_predict",
     "sb_vfe_destroy",
@@ -118,6 +119,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = i32
+    lib.sb_owner_of_block.argtypes, lib.sb_owner_of_block.restype = [i64, i32], i32
+    lib.sb_owned_trailing_tiles.argtypes, lib.sb_owned_trailing_tiles.restype = [i64, i64, i32, i32], i64
+    lib.sb_row_chunk.argtypes, lib.sb_row_chunk.restype = [i64, i32, i32, P(i64), P(i64)], i32
     if lib.sb_abi_version() != 1:
         raise ImportError("libstheno_b200 ABI version mismatch")
     _lib = lib
