@@ -200,10 +200,12 @@ int32_t sb_factor_get_L(sb_ctx* ctx, sb_factor* f, void* L_out);
 /* ---- VFE / elbo --------------------------------------------------------------------------
  * Replaces AbstractGPs elbo/dtc/posterior(VFE(fz), fx, y) reached through
  * src/gp/sparse_finite_gp.jl:52-62.  uu = cov(fz) (symmetric spec, M x M) with its jitter
- * noise_u; uf = cov(f, z, x) dense spec (M x N); ff_diag = var(f, x) diag spec; noise_f the
- * (diagonal) observation noise; delta = y - m(x). out2 = {elbo, dtc}. */
+ * noise_u; xu = cov(f, x, z) dense spec (N x M, all blocks); ff_diag = var(f, x) diag spec;
+ * noise_f the (diagonal) observation noise; delta = y - m(x).  out2 = {elbo, dtc}.
+ * K_fu is streamed in row chunks and never held whole; multi-GPU: chunks are sharded and the
+ * M x M accumulator is all-reduced. */
 int32_t sb_vfe_create(sb_ctx* ctx, const sb_covspec* uu, const sb_noise* noise_u,
-                      const sb_covspec* uf, const sb_covspec* ff_diag, const sb_noise* noise_f,
+                      const sb_covspec* xu, const sb_covspec* ff_diag, const sb_noise* noise_f,
                       const void* delta, sb_vfe** out, double* out2, int64_t* info);
 int32_t sb_vfe_predict(sb_ctx* ctx, sb_vfe* v, const sb_covspec* cross /* N* x M */,
                        const sb_covspec* prior_diag, void* mean_out, void* var_out);

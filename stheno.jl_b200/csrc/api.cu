@@ -337,8 +337,9 @@ static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, si
     return SB_OK;
 }
 
-int32_t cholesky_packed(sb_ctx* c, sb_factor* f) {
+int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     const int64_t nblk = f->L.nblk();
+    const int world = force_local ? 1 : c->world, rank = force_local ? 0 : c->rank;
     const int64_t Np = f->Np;
     cudaStream_t st = c->stream;
     const bool ft = c->fine_timing;
@@ -358,16 +359,16 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f) {
     for (int64_t k0 = 0; k0 < nblk; k0 += 2) {
         const int64_t k1 = k0 + 1;
         const int64_t m0 = Np - (k0 + 1) * NB;
-        const int own0 = (int)(k0 % c->world), own1 = (int)(k1 % c->world);
+        const int own0 = (int)(k0 % world), own1 = (int)(k1 % world);
         markk(3);
-        if (own0 == c->rank) {
+        if (own0 == rank) {
             launch_potrf_inv(f->L, k0, f->N, f->invL, f->logdet_blk, f->info_dev, st);
             if (m0 > 0)
                 launch_gemm_nt(f->L.blk(k0 + 1, k0), f->L.ld(k0), f->invL + k0 * (int64_t)NB * NB, NB, Pc, m0,
                                m0, NB, NB, 1.0, 0.0, st);
         }
         markk(0);
-        if (c->world > 1) SB_TRY(bcast_panel(c, f, k0, Pc, (size_t)m0 * NB, own0));
+        if (world > 1) SB_TRY(bcast_panel(c, f, k0, Pc, (size_t)m0 * NB, own0));
         markk(1);
         if (m0 <= 0) break;
         SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k0 + 1, k0), f->L.ld(k0) * sizeof(double), Pc, m0 * sizeof(double),
@@ -375,22 +376,22 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f) {
         // second half panel: block column k1 gets the k0 update first, then is factored
         const int64_t m1 = m0 - NB;
         double* P2 = Pc + (int64_t)NB * m0 + NB;  // column 128, row offset 128 (row 0 <-> block row k1)
-        if (own1 == c->rank) {
-            launch_syrk_packed(f->L, k0, Pc, NB, k1, k1 + 1, c->rank, c->world, st);
+        if (own1 == rank) {
+            launch_syrk_packed(f->L, k0, Pc, NB, k1, k1 + 1, rank, world, st);
             launch_potrf_inv(f->L, k1, f->N, f->invL, f->logdet_blk, f->info_dev, st);
             if (m1 > 0)
                 launch_gemm_nt(f->L.blk(k1 + 1, k1), f->L.ld(k1), f->invL + k1 * (int64_t)NB * NB, NB, P2, m0,
                                m1, NB, NB, 1.0, 0.0, st);
         }
         markk(0);
-        if (c->world > 1) SB_TRY(bcast_panel(c, f, k1, Pc + (int64_t)NB * m0, m1 > 0 ? (size_t)m0 * NB : 0, own1));
+        if (world > 1) SB_TRY(bcast_panel(c, f, k1, Pc + (int64_t)NB * m0, m1 > 0 ? (size_t)m0 * NB : 0, own1));
         markk(1);
         if (m1 > 0) {
             SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k1 + 1, k1), f->L.ld(k1) * sizeof(double), P2, m0 * sizeof(double),
                                       m1 * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
-            int64_t tiles = syrk_packed_tiles(nblk, k0, k1 + 1, nblk, c->rank, c->world);
+            int64_t tiles = syrk_packed_tiles(nblk, k0, k1 + 1, nblk, rank, world);
             markk(0);
-            launch_syrk_packed(f->L, k0, Pc, 2 * NB, k1 + 1, nblk, c->rank, c->world, st);
+            launch_syrk_packed(f->L, k0, Pc, 2 * NB, k1 + 1, nblk, rank, world, st);
             markk(2);
             if (tiles > 0) {
                 flops += (double)tiles * 2.0 * NB * NB * (2.0 * NB);
@@ -398,17 +399,17 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f) {
             }
         }
     }
-    if (c->world > 1) {
+    if (world > 1) {
         // the diagonal blocks themselves live only on their owners so far: share them so every
         // rank holds the complete factor (needed by the replicated / RHS-sharded solves)
         for (int64_t k = 0; k < nblk; k++) {
-            int owner = (int)(k % c->world);
+            int owner = (int)(k % world);
             double* tmp = f->panel;  // pack L_kk (NB columns strided by ld(k)) through the panel buffer
-            if (owner == c->rank)
+            if (owner == rank)
                 SB_CUDA(cudaMemcpy2DAsync(tmp, NB * sizeof(double), f->L.blk(k, k), f->L.ld(k) * sizeof(double),
                                           NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
             SB_NCCL(nccl_dl::Broadcast(tmp, tmp, (size_t)NB * NB, ncclDouble, owner, c->comm, st));
-            if (owner != c->rank)
+            if (owner != rank)
                 SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k, k), f->L.ld(k) * sizeof(double), tmp, NB * sizeof(double),
                                           NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
         }
@@ -634,8 +635,66 @@ int32_t sb_factor_destroy(sb_factor* f) {
     return SB_OK;
 }
 
+static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_noise* noise, sb_factor** out,
+                                  int64_t* info, bool force_local);
+
 int32_t sb_factor_create(sb_ctx* c, const sb_covspec* spec, const sb_noise* noise, sb_factor** out,
                          int64_t* info) {
+    return factor_create_impl(c, spec, noise, out, info, false);
+}
+
+// allocate the buffers of a factor of order N from the context pool
+static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
+    sb_factor* f = new sb_factor();
+    f->ctx = c;
+    f->N = N;
+    f->Np = round_up(N, NB);
+    f->L.Np = f->Np;
+    const int64_t nblk = f->L.nblk();
+    f->bytes_L = (size_t)f->L.total() * sizeof(double);
+    f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
+    f->bytes_ld = (size_t)nblk * sizeof(double);
+    f->bytes_panel = (size_t)2 * f->Np * NB * sizeof(double);
+    f->bytes_alpha = (size_t)f->Np * sizeof(double);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->L.base, f->bytes_L);
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->invL, f->bytes_invL);
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->logdet_blk, f->bytes_ld);
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->info_dev, 8);
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->panel, f->bytes_panel);
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->alpha, f->bytes_alpha);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream);
+    if (e != cudaSuccess) {
+        sb_factor_destroy(f);
+        return sb::cuda_fail(e, "factor_alloc", __FILE__, __LINE__);
+    }
+    *out = f;
+    return SB_OK;
+}
+
+// run the Cholesky on an assembled packed matrix and collect info / logdet
+static int32_t factor_finish(sb_ctx* c, sb_factor* f, int64_t* info, bool force_local) {
+    SB_TRY(cholesky_packed(c, f, force_local));
+    const int64_t nblk = f->L.nblk();
+    long long h_info = 0;
+    std::vector<double> ld(nblk);
+    SB_CUDA(cudaMemcpy(&h_info, f->info_dev, sizeof(long long), cudaMemcpyDeviceToHost));
+    SB_CUDA(cudaMemcpy(ld.data(), f->logdet_blk, nblk * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_info != 0) {
+        if (info) *info = (int64_t)h_info;
+        sb::set_error("matrix is not positive definite; Cholesky factorization failed at pivot " +
+                      std::to_string(h_info));
+        return SB_ERR_NOT_POSDEF;
+    }
+    double sum = 0.0;
+    for (double v : ld) sum += v;
+    f->logdet = sum;
+    return SB_OK;
+}
+
+static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_noise* noise, sb_factor** out,
+                                  int64_t* info, bool force_local) {
     SB_CHECK(c && spec && out, "null argument");
     SB_CHECK(spec->symmetric == 1 && spec->nrows == spec->ncols, "factor needs a symmetric square spec");
     SB_CHECK(spec->nrows > 0, "empty matrix");
@@ -698,7 +757,7 @@ int32_t sb_factor_create(sb_ctx* c, const sb_covspec* spec, const sb_noise* nois
         launch_fill_padding(f->L, f->N, c->stream);
         t.stop();
         SB_CUDA_F(cudaGetLastError());
-        int32_t s = cholesky_packed(c, f);
+        int32_t s = cholesky_packed(c, f, force_local);
         if (s != SB_OK) return fail(s);
         t.collect();
     }
@@ -781,6 +840,26 @@ int32_t sb_factor_alpha(sb_ctx* c, sb_factor* f, void* alpha_out) {
     SB_CHECK(f->has_alpha, "sb_factor_set_data has not been called");
     begin_call(c);
     SB_CUDA(cudaMemcpy(alpha_out, f->alpha, f->N * sizeof(double), cudaMemcpyDefault));
+    return SB_OK;
+}
+
+// W <- W L^{-T} (rows_p x Np, ld rows_p): right-looking block forward substitution, tensor-core
+// products only.  keep: write the result back into W; acc != null: acc[r] += sum_c result[r,c]^2.
+static int32_t trsm_sweep(sb_ctx* c, sb_factor* f, double* W, int64_t rows_p, double* Xk, bool keep, double* acc) {
+    const int64_t nblk = f->L.nblk(), Np = f->Np;
+    for (int64_t k = 0; k < nblk; k++) {
+        double* Wk = W + k * NB * rows_p;
+        launch_gemm_nt(Wk, rows_p, f->invL + k * (int64_t)NB * NB, NB, Xk, rows_p, rows_p, NB, NB, 1.0, 0.0,
+                       c->stream);
+        if (keep)
+            SB_CUDA(cudaMemcpyAsync(Wk, Xk, (size_t)rows_p * NB * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (acc) launch_rowsumsq_acc(Xk, rows_p, rows_p, NB, acc, c->stream);
+        int64_t m = Np - (k + 1) * NB;
+        if (m > 0)
+            launch_gemm_nt(Xk, rows_p, f->L.blk(k + 1, k), f->L.ld(k), W + (k + 1) * NB * rows_p, rows_p, rows_p, m,
+                           NB, -1.0, 1.0, c->stream);
+    }
+    SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
 
@@ -942,15 +1021,208 @@ int32_t sb_factor_get_L(sb_ctx* c, sb_factor* f, void* L_out) {
     return SB_OK;
 }
 
-int32_t sb_vfe_create(sb_ctx*, const sb_covspec*, const sb_noise*, const sb_covspec*,
-                      const sb_covspec*, const sb_noise*, const void*, sb_vfe**, double*, int64_t*) {
-    sb::set_error("VFE/elbo path is not built yet");
-    return SB_ERR_UNSUPPORTED;
+struct sb_vfe {
+    sb_ctx* ctx = nullptr;
+    sb_factor* fu = nullptr;  // chol(K_uu + jitter)
+    sb_factor* fl = nullptr;  // chol(A A^T + I)
+    double* alpha = nullptr;  // Mp, K_*u alpha = posterior mean
+    size_t bytes_alpha = 0;
+    int64_t M = 0, Mp = 0;
+};
+
+int32_t sb_vfe_destroy(sb_vfe* v) {
+    if (!v) return SB_OK;
+    if (v->fu) sb_factor_destroy(v->fu);
+    if (v->fl) sb_factor_destroy(v->fl);
+    if (v->alpha) v->ctx->pool_release(v->alpha, v->bytes_alpha);
+    delete v;
+    return SB_OK;
 }
-int32_t sb_vfe_predict(sb_ctx*, sb_vfe*, const sb_covspec*, const sb_covspec*, void*, void*) {
-    sb::set_error("VFE/elbo path is not built yet");
-    return SB_ERR_UNSUPPORTED;
+
+// Titsias VFE (AbstractGPs `_compute_intermediates`), streamed over row chunks of
+// the observations so K_fu is never held whole:  per chunk  W = Sigma^{-1/2} K_fu  ->  W L_u^{-T}
+// (= A^T rows)  ->  D += A A^T,  v += A delta~,  |A|_F^2.   Multi-GPU: chunks are sharded over
+// ranks and D, v, |A|_F^2 are all-reduced (the only collective); the two M x M Choleskys are
+// replicated.
+int32_t sb_vfe_create(sb_ctx* c, const sb_covspec* uu, const sb_noise* noise_u, const sb_covspec* xu,
+                      const sb_covspec* ff_diag, const sb_noise* noise_f, const void* delta, sb_vfe** out,
+                      double* out2, int64_t* info) {
+    SB_CHECK(c && uu && xu && ff_diag && noise_f && delta && out && out2, "null argument");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    *out = nullptr;
+    if (info) *info = 0;
+    const int64_t N = xu->nrows, M = xu->ncols;
+    SB_CHECK(uu->nrows == M && uu->symmetric == 1, "uu must be the symmetric M x M spec of cov(fz)");
+    SB_CHECK(ff_diag->nrows == N, "ff_diag must have N rows");
+    SB_CHECK(N > 0 && M > 0, "empty problem");
+    cudaEvent_t t0 = c->next_event(), t1 = c->next_event();
+    cudaEventRecord(t0, c->stream);
+
+    sb_vfe* v = new sb_vfe();
+    v->ctx = c;
+    auto fail = [&](int32_t st) { sb_vfe_destroy(v); return st; };
+    int32_t st = factor_create_impl(c, uu, noise_u, &v->fu, info, /*force_local=*/true);
+    if (st != SB_OK) return fail(st);
+    begin_call(c);  // factor_create_impl reset the event pool; keep our own markers valid
+    t0 = c->next_event(); t1 = c->next_event();
+    cudaEventRecord(t0, c->stream);
+    v->M = M;
+    v->Mp = v->fu->Np;
+    const int64_t Mp = v->Mp;
+
+    // host O(N) prep: sigma^{-1}, delta~ = delta / sigma, log det Sigma_y, |delta~|^2
+    std::vector<double> hd(N), sinv(N), hnoise(N);
+    if (cudaMemcpy(hd.data(), delta, N * sizeof(double), cudaMemcpyDefault) != cudaSuccess) return fail(SB_ERR_CUDA);
+    if (noise_f->diag) {
+        if (cudaMemcpy(hnoise.data(), noise_f->diag, N * sizeof(double), cudaMemcpyDefault) != cudaSuccess) return fail(SB_ERR_CUDA);
+    } else {
+        for (int64_t i = 0; i < N; i++) hnoise[i] = noise_f->sigma2;
+    }
+    double logdet_sy = 0.0, dd = 0.0;
+    for (int64_t i = 0; i < N; i++) {
+        if (!(hnoise[i] > 0.0)) { sb::set_error("VFE needs positive observation noise"); return fail(SB_ERR_INVALID); }
+        sinv[i] = 1.0 / sqrt(hnoise[i]);
+        logdet_sy += log(hnoise[i]);
+        hd[i] *= sinv[i];
+        dd += hd[i] * hd[i];
+    }
+
+    DevSpec dxu(c), dff(c);
+    if ((st = dxu.build(xu, c->stream, false)) != SB_OK) return fail(st);
+    if ((st = dff.build(ff_diag, c->stream, true)) != SB_OK) return fail(st);
+    const std::vector<BlockDev> all_blocks = dxu.blocks;
+
+    const int64_t NC = 16384;  // observation rows per chunk
+    DevBuf dsinv(c), ddt(c), W(c), T(c), Xk(c), D(c), vv(c), fro(c), varf(c);
+    const int64_t nchunks_total = (N + NC - 1) / NC;
+#define VFE_TRY(expr) do { int32_t _s = (expr); if (_s != SB_OK) return fail(_s); } while (0)
+#define VFE_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(sb::cuda_fail(_e, #call, __FILE__, __LINE__)); } while (0)
+    VFE_TRY(dsinv.alloc(N * sizeof(double)));
+    VFE_TRY(ddt.alloc(round_up(N, NC) * sizeof(double)));
+    VFE_TRY(W.alloc((size_t)NC * Mp * sizeof(double)));
+    VFE_TRY(T.alloc((size_t)NC * Mp * sizeof(double)));
+    VFE_TRY(Xk.alloc((size_t)NC * NB * sizeof(double)));
+    VFE_TRY(D.alloc((size_t)Mp * Mp * sizeof(double)));
+    VFE_TRY(vv.alloc((size_t)(Mp + 8) * sizeof(double)));
+    VFE_TRY(fro.alloc((size_t)(nchunks_total + 1) * sizeof(double)));
+    VFE_TRY(varf.alloc(N * sizeof(double)));
+    VFE_CUDA(cudaMemcpyAsync(dsinv.p, sinv.data(), N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VFE_CUDA(cudaMemsetAsync(ddt.p, 0, round_up(N, NC) * sizeof(double), c->stream));
+    VFE_CUDA(cudaMemcpyAsync(ddt.p, hd.data(), N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VFE_CUDA(cudaMemsetAsync(D.p, 0, (size_t)Mp * Mp * sizeof(double), c->stream));
+    VFE_CUDA(cudaMemsetAsync(vv.p, 0, (size_t)(Mp + 8) * sizeof(double), c->stream));
+    VFE_CUDA(cudaMemsetAsync(fro.p, 0, (size_t)(nchunks_total + 1) * sizeof(double), c->stream));
+
+    for (int64_t ci = c->rank; ci < nchunks_total; ci += c->world) {  // chunks round-robin over ranks
+        const int64_t r0 = ci * NC, r1 = r0 + NC < N ? r0 + NC : N;
+        const int64_t rows = r1 - r0, rows_p = round_up(rows, NB);
+        dxu.blocks = all_blocks;
+        dxu.nrows = N;
+        clip_rows(dxu, r0, r1, false);
+        VFE_CUDA(cudaMemsetAsync(W.p, 0, (size_t)rows_p * Mp * sizeof(double), c->stream));
+        VFE_TRY(assemble_dense(c, dxu, W.d(), rows_p));
+        launch_rowscale(W.d(), rows_p, rows, Mp, dsinv.d() + r0, c->stream);
+        VFE_TRY(trsm_sweep(c, v->fu, W.d(), rows_p, Xk.d(), /*keep=*/true, nullptr));
+        launch_colsumsq(W.d(), rows_p * Mp, 0, 1, fro.d() + ci, c->stream);
+        launch_gemv_t(W.d(), rows_p, rows, Mp, ddt.d() + r0, vv.d(), c->stream);
+        launch_transpose(W.d(), rows_p, rows_p, Mp, T.d(), Mp, c->stream);
+        launch_gemm_nt(T.d(), Mp, T.d(), Mp, D.d(), Mp, Mp, Mp, rows_p, 1.0, 1.0, c->stream);
+    }
+    VFE_CUDA(cudaGetLastError());
+    if (c->world > 1) {
+        auto nc = [&](ncclResult_t r) { if (r != ncclSuccess) { sb::set_error("NCCL all-reduce failed in VFE"); return false; } return true; };
+        if (!nc(nccl_dl::AllReduce(D.p, D.p, (size_t)Mp * Mp, ncclDouble, ncclSum, c->comm, c->stream))) return fail(SB_ERR_NCCL);
+        if (!nc(nccl_dl::AllReduce(vv.p, vv.p, (size_t)Mp, ncclDouble, ncclSum, c->comm, c->stream))) return fail(SB_ERR_NCCL);
+        if (!nc(nccl_dl::AllReduce(fro.p, fro.p, (size_t)nchunks_total, ncclDouble, ncclSum, c->comm, c->stream))) return fail(SB_ERR_NCCL);
+    }
+    // Lambda = chol(D + I)
+    VFE_TRY(factor_alloc(c, M, &v->fl));
+    launch_pack_lower(v->fl->L, D.d(), Mp, 1.0, c->stream);
+    // (padding rows/cols of D are zero: +1 on the diagonal makes them identity)
+    VFE_CUDA(cudaGetLastError());
+    st = factor_finish(c, v->fl, info, /*force_local=*/true);
+    if (st != SB_OK) return fail(st);
+    // w = L_Lambda^{-1} (A delta~)
+    DevBuf q(c);
+    VFE_TRY(q.alloc(sizeof(double)));
+    forward_solve(c, v->fl, vv.d(), 1);
+    launch_colsumsq(vv.d(), Mp, Mp, 1, q.d(), c->stream);
+    // var(f, x) for the trace term
+    VFE_CUDA(cudaMemsetAsync(varf.p, 0, N * sizeof(double), c->stream));
+    VFE_TRY(assemble_diag(c, dff, varf.d()));
+    std::vector<double> hvar(N), hfro(nchunks_total);
+    double hq = 0.0;
+    VFE_CUDA(cudaMemcpyAsync(hvar.data(), varf.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VFE_CUDA(cudaMemcpyAsync(hfro.data(), fro.p, nchunks_total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VFE_CUDA(cudaMemcpyAsync(&hq, q.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // posterior weights: m_eps = L_Lambda^{-T} w ; alpha = L_u^{-T} m_eps
+    backward_solve(c, v->fl, vv.d(), 1);
+    backward_solve(c, v->fu, vv.d(), 1);
+    v->bytes_alpha = (size_t)Mp * sizeof(double);
+    VFE_CUDA(c->pool_alloc((void**)&v->alpha, v->bytes_alpha));
+    VFE_CUDA(cudaMemcpyAsync(v->alpha, vv.p, v->bytes_alpha, cudaMemcpyDeviceToDevice, c->stream));
+    VFE_CUDA(cudaGetLastError());
+    cudaEventRecord(t1, c->stream);
+    VFE_CUDA(cudaStreamSynchronize(c->stream));
+    double tr = 0.0, fro_sum = 0.0;
+    for (int64_t i = 0; i < N; i++) tr += hvar[i] / hnoise[i];
+    for (double x : hfro) fro_sum += x;
+    const double log2pi = 1.8378770664093454835606594728112;
+    const double dtc = -((double)N * log2pi + logdet_sy + v->fl->logdet + dd - hq) / 2.0;
+    out2[0] = dtc - (tr - fro_sum) / 2.0;  // elbo
+    out2[1] = dtc;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    c->tm.total_ms += ms;
+    count_launches(c, before);
+    *out = v;
+    return SB_OK;
+#undef VFE_TRY
+#undef VFE_CUDA
 }
-int32_t sb_vfe_destroy(sb_vfe*) { return SB_OK; }
+
+int32_t sb_vfe_predict(sb_ctx* c, sb_vfe* v, const sb_covspec* cross, const sb_covspec* prior_diag,
+                       void* mean_out, void* var_out) {
+    SB_CHECK(c && v && cross, "null argument");
+    SB_CHECK(cross->ncols == v->M, "cross spec must be N* x M");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    const int64_t Ns = cross->nrows, Nsp = round_up(Ns > 0 ? Ns : 1, NB), Mp = v->Mp;
+    if (Ns == 0) return SB_OK;
+    DevSpec dc(c), dp(c);
+    SB_TRY(dc.build(cross, c->stream, false));
+    DevBuf W(c), Xk(c), mean(c), acc1(c), acc2(c), pd(c);
+    SB_TRY(W.alloc((size_t)Nsp * Mp * sizeof(double)));
+    SB_CUDA(cudaMemsetAsync(W.p, 0, (size_t)Nsp * Mp * sizeof(double), c->stream));
+    SB_TRY(assemble_dense(c, dc, W.d(), Nsp));
+    if (mean_out) {
+        SB_TRY(mean.alloc(Nsp * sizeof(double)));
+        launch_gemv_n(W.d(), Nsp, Nsp, Mp, v->alpha, mean.d(), c->stream);
+        SB_CUDA(cudaMemcpyAsync(mean_out, mean.p, Ns * sizeof(double), cudaMemcpyDefault, c->stream));
+    }
+    if (var_out) {
+        SB_CHECK(prior_diag && prior_diag->nrows == Ns, "prior diag spec required for var");
+        SB_TRY(dp.build(prior_diag, c->stream, true));
+        SB_TRY(Xk.alloc((size_t)Nsp * NB * sizeof(double)));
+        SB_TRY(acc1.alloc(Nsp * sizeof(double)));
+        SB_TRY(acc2.alloc(Nsp * sizeof(double)));
+        SB_TRY(pd.alloc(Nsp * sizeof(double)));
+        SB_CUDA(cudaMemsetAsync(acc1.p, 0, Nsp * sizeof(double), c->stream));
+        SB_CUDA(cudaMemsetAsync(acc2.p, 0, Nsp * sizeof(double), c->stream));
+        SB_CUDA(cudaMemsetAsync(pd.p, 0, Nsp * sizeof(double), c->stream));
+        // B^T = K_*u L_u^{-T} (kept), then (L_Lambda^{-1} B)^T = B^T L_Lambda^{-T}
+        SB_TRY(trsm_sweep(c, v->fu, W.d(), Nsp, Xk.d(), true, acc1.d()));
+        SB_TRY(trsm_sweep(c, v->fl, W.d(), Nsp, Xk.d(), false, acc2.d()));
+        SB_TRY(assemble_diag(c, dp, pd.d()));
+        launch_sub(pd.d(), pd.d(), acc1.d(), Ns, c->stream);    // k** - |B|^2
+        launch_axpy1(pd.d(), acc2.d(), Ns, c->stream);          //     + |L_Lambda^{-1} B|^2
+        SB_CUDA(cudaMemcpyAsync(var_out, pd.p, Ns * sizeof(double), cudaMemcpyDefault, c->stream));
+    }
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    count_launches(c, before);
+    return SB_OK;
+}
 
 }  // extern "C"

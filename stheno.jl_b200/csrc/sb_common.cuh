@@ -127,10 +127,19 @@ void launch_gemv_n(const double* W, int64_t ld, int64_t M, int64_t n, const doub
 void launch_rowsumsq_acc(const double* X, int64_t ld, int64_t M, int64_t ncols, double* acc,
                          cudaStream_t s);
 void launch_sub(double* out, const double* a, const double* b, int64_t n, cudaStream_t s);
+void launch_axpy1(double* y, const double* x, int64_t n, cudaStream_t s);
 // dense lower-triangular L (N x N, ld N) from packed
 void launch_unpack_lower(Packed L, int64_t N, double* out, cudaStream_t s);
 // out[N x S] = L * z   (z: N x S, ld Np) -- used by sb_rand
 void launch_trmv_lower(Packed L, int64_t N, const double* z, double* out, int S, cudaStream_t s);
+
+// VFE helpers
+void launch_rowscale(double* W, int64_t ld, int64_t rows, int64_t cols, const double* s, cudaStream_t st);
+void launch_gemv_t(const double* W, int64_t ld, int64_t rows, int64_t cols, const double* x, double* y,
+                   cudaStream_t st);
+void launch_transpose(const double* in, int64_t ld_in, int64_t rows, int64_t cols, double* out,
+                      int64_t ld_out, cudaStream_t st);
+void launch_pack_lower(Packed L, const double* D, int64_t ld, double shift, cudaStream_t st);
 
 extern thread_local int64_t g_launch_count;
 

@@ -154,6 +154,11 @@ rowsumsq_acc_kernel(const double* __restrict__ X, int64_t ld, int64_t M, int64_t
     atomicAdd(&acc_out[r], acc);
 }
 
+__global__ void axpy1_kernel(double* y, const double* x, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
 __global__ void sub_kernel(double* out, const double* a, const double* b, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] - b[i];
@@ -187,7 +192,81 @@ trmv_lower_kernel(Packed L, int64_t N, const double* __restrict__ z, double* __r
     }
 }
 
+// W[r, c] *= s[r]
+__global__ void __launch_bounds__(256)
+rowscale_kernel(double* __restrict__ W, int64_t ld, int64_t rows, const double* __restrict__ s) {
+    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= rows) return;
+    W[(int64_t)blockIdx.y * ld + r] *= s[r];
+}
+
+// y[c] += sum_r W[r, c] * x[r]   (columns are contiguous: one warp per column chunk)
+__global__ void __launch_bounds__(256)
+gemv_t_kernel(const double* __restrict__ W, int64_t ld, int64_t rows, const double* __restrict__ x,
+              double* __restrict__ y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.y * 8 + warp;
+    const int64_t r0 = (int64_t)blockIdx.x * 4096;
+    const int64_t r1 = r0 + 4096 < rows ? r0 + 4096 : rows;
+    const double* col = W + c * ld;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int64_t r = r0 + lane; r < r1; r += 32) acc = fma(col[r], x[r], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) atomicAdd(&y[c], acc);
+}
+
+// out[c, r] = in[r, c]  (in: rows x cols, ld_in; out: cols x rows, ld_out), 32x32 smem tiles
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ in, int64_t ld_in, double* __restrict__ out, int64_t ld_out) {
+    __shared__ double t[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) t[j][tx] = in[(c0 + j) * ld_in + r0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) out[(r0 + j) * ld_out + c0 + tx] = t[tx][j];
+}
+
+// packed lower <- dense (n x n, ld), plus `shift` added on the diagonal
+__global__ void __launch_bounds__(256)
+pack_lower_kernel(Packed L, const double* __restrict__ D, int64_t ld, double shift) {
+    int64_t c = blockIdx.y;
+    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= L.Np || r / NB < c / NB) return;
+    double v = D[c * ld + r];
+    if (r == c) v += shift;
+    *L.at(r, c) = v;
+}
+
 }  // namespace
+
+void launch_rowscale(double* W, int64_t ld, int64_t rows, int64_t cols, const double* s, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return;
+    rowscale_kernel<<<dim3((unsigned)((rows + 255) / 256), (unsigned)cols), 256, 0, st>>>(W, ld, rows, s);
+    g_launch_count++;
+}
+
+void launch_gemv_t(const double* W, int64_t ld, int64_t rows, int64_t cols, const double* x, double* y,
+                   cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return;  // cols must be a multiple of 8
+    gemv_t_kernel<<<dim3((unsigned)((rows + 4095) / 4096), (unsigned)(cols / 8)), 256, 0, st>>>(W, ld, rows, x, y);
+    g_launch_count++;
+}
+
+void launch_transpose(const double* in, int64_t ld_in, int64_t rows, int64_t cols, double* out, int64_t ld_out,
+                      cudaStream_t st) {
+    // rows, cols multiples of 32
+    transpose_kernel<<<dim3((unsigned)(rows / 32), (unsigned)(cols / 32)), 256, 0, st>>>(in, ld_in, out, ld_out);
+    g_launch_count++;
+}
+
+void launch_pack_lower(Packed L, const double* D, int64_t ld, double shift, cudaStream_t st) {
+    pack_lower_kernel<<<dim3((unsigned)((L.Np + 255) / 256), (unsigned)L.Np), 256, 0, st>>>(L, D, ld, shift);
+    g_launch_count++;
+}
 
 void launch_trsv_diag(const double* invLk, double* bk, int64_t ldb, int S, bool transpose,
                       cudaStream_t s) {
@@ -229,6 +308,12 @@ void launch_rowsumsq_acc(const double* X, int64_t ld, int64_t M, int64_t ncols, 
                          cudaStream_t s) {
     dim3 grid((unsigned)((M + 255) / 256), (unsigned)((ncols + 31) / 32));
     rowsumsq_acc_kernel<<<grid, 256, 0, s>>>(X, ld, M, ncols, acc);
+    g_launch_count++;
+}
+
+void launch_axpy1(double* y, const double* x, int64_t n, cudaStream_t s) {
+    if (n <= 0) return;
+    axpy1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, x, n);
     g_launch_count++;
 }
 

@@ -353,7 +353,7 @@ def _vfe_create(v: VFE, fx: FiniteGP, y):
         raise ValueError("DimensionMismatch: length(y) != length(fx)")
     lz, lx = fz.lowered, fx.lowered
     uu = spec_symmetric(lz)
-    uf = spec_dense(lz, lx)
+    xu = spec_dense(lx, lz)
     ffd = spec_diag(lx)
     nu, nf = _noise_struct(fz.noise, lz.n), _noise_struct(fx.noise, lx.n)
     delta = np.ascontiguousarray(y - lx.mean())
@@ -361,7 +361,7 @@ def _vfe_create(v: VFE, fx: FiniteGP, y):
     out2 = (C.c_double * 2)()
     info = C.c_int64(0)
     ctx = _ctx()
-    st = _lib.load().sb_vfe_create(ctx.h, C.byref(uu), C.byref(nu), C.byref(uf), C.byref(ffd), C.byref(nf),
+    st = _lib.load().sb_vfe_create(ctx.h, C.byref(uu), C.byref(nu), C.byref(xu), C.byref(ffd), C.byref(nf),
                                    delta.ctypes.data, C.byref(h), out2, C.byref(info))
     _lib.check(st, info)
     return _VfeHandle(h, ctx), out2[0], out2[1]

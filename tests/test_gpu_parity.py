@@ -175,3 +175,53 @@ def test_factorisation_is_race_free_and_deterministic(sb):
         if ref is None:
             ref = L
         assert np.array_equal(L, ref)
+
+
+@pytest.mark.parametrize("n,m", [(700, 50), (5000, 300), (20000, 130)])
+def test_vfe_elbo_and_approx_posterior(sb, orc, n, m):
+    """elbo / dtc / approximate posterior (AbstractGPs VFE via src/gp/sparse_finite_gp.jl:52-62)."""
+    rng = np.random.default_rng(n + m)
+    x = rng.uniform(0, 30, n)
+    z = np.linspace(0, 30, m)
+    xs = rng.uniform(0, 30, 150)
+    y = np.sin(x) + 0.3 * rng.standard_normal(n)
+    noise = rng.uniform(0.05, 0.15, n) if n == 700 else 0.1
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    fxs, fzs = fs(sb.GPPPInput("f", x), noise), fs(sb.GPPPInput("f", z), 1e-6)
+    fxo, fzo = fo(orc.GPPPInput("f", x), noise), fo(orc.GPPPInput("f", z), 1e-6)
+    e, eo = sb.elbo(sb.VFE(fzs), fxs, y), orc.elbo(orc.VFE(fzo), fxo, y)
+    np.testing.assert_allclose(e, eo, rtol=1e-9)
+    np.testing.assert_allclose(sb.dtc(sb.VFE(fzs), fxs, y), orc.dtc(orc.VFE(fzo), fxo, y), rtol=1e-9)
+    sp = sb.SparseFiniteGP(fxs, fzs)
+    np.testing.assert_allclose(sb.logpdf(sp, y), sb.elbo(sp, y), rtol=1e-13)  # atomics: last-ulp run-to-run
+    ps, po = sb.posterior(sp, y), orc.posterior(orc.SparseFiniteGP(fxo, fzo), y)
+    mm, vv = sb.mean_and_var(ps, sb.GPPPInput("f", xs))
+    np.testing.assert_allclose(mm, orc.mean(po, orc.GPPPInput("f", xs)), rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(vv, orc.var(po, orc.GPPPInput("f", xs)), rtol=1e-6, atol=1e-8)
+
+
+def test_vfe_relations(sb):
+    """README.md:75-78: pseudo-points == observations => elbo == logpdf; and logpdf > elbo
+    (test/gp/sparse_finite_gp.jl:40-41)."""
+    rng = np.random.default_rng(77)
+    x = rng.uniform(0, 5, 300)
+    y = np.sin(x) + 0.3 * rng.standard_normal(300)
+    f = sb.gppp(lambda GP: dict(f=GP(sb.Matern32Kernel())))
+    fx = f(sb.GPPPInput("f", x), 0.1)
+    lp = sb.logpdf(fx, y)
+    assert abs(sb.elbo(sb.VFE(f(sb.GPPPInput("f", x), 1e-10)), fx, y) - lp) < 1e-5 * abs(lp)
+    assert lp > sb.elbo(sb.VFE(f(sb.GPPPInput("f", x[::10]), 1e-9)), fx, y)
+
+
+def test_vfe_pseudo_points_in_other_processes(sb, orc):
+    """examples/gppp_and_pseudo_points/script.jl:114-121: observe f3 = f1 + f2, pseudo-points in f1 and f2."""
+    rng = np.random.default_rng(5)
+    fs, fo = both(sb, orc, f3_model)
+    x = rng.uniform(0, 10, 900)
+    z = np.linspace(0, 10, 40)
+    y = rng.standard_normal(900)
+    zs = sb.BlockData(sb.GPPPInput("f1", z), sb.GPPPInput("f2", z))
+    zo = orc.BlockData(orc.GPPPInput("f1", z), orc.GPPPInput("f2", z))
+    e = sb.elbo(sb.VFE(fs(zs, 1e-6)), fs(sb.GPPPInput("f3", x), 0.2), y)
+    eo = orc.elbo(orc.VFE(fo(zo, 1e-6)), fo(orc.GPPPInput("f3", x), 0.2), y)
+    np.testing.assert_allclose(e, eo, rtol=1e-9)
