@@ -355,7 +355,9 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     auto markk = [&](int kind) { if (ft) { mark(); evkind.push_back(kind); } };
     double flops = 0;
     int64_t nlaunch = 0;
-    double* Pc = f->panel;
+    // two half panels in TILED layout (gemm_nt.cu); row block 0 <-> block row k0+1
+    double* P1t = f->panel;
+    double* P2t = f->panel + tiled_panel_elems(Np);
     for (int64_t k0 = 0; k0 < nblk; k0 += 2) {
         const int64_t k1 = k0 + 1;
         const int64_t m0 = Np - (k0 + 1) * NB;
@@ -364,34 +366,30 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
         if (own0 == rank) {
             launch_potrf_inv(f->L, k0, f->N, f->invL, f->logdet_blk, f->info_dev, st);
             if (m0 > 0)
-                launch_gemm_nt(f->L.blk(k0 + 1, k0), f->L.ld(k0), f->invL + k0 * (int64_t)NB * NB, NB, Pc, m0,
-                               m0, NB, NB, 1.0, 0.0, st);
+                launch_trsm_tiled(f->L.blk(k0 + 1, k0), f->L.ld(k0), f->invL + k0 * (int64_t)NB * NB, P1t, m0, st);
         }
         markk(0);
-        if (world > 1) SB_TRY(bcast_panel(c, f, k0, Pc, (size_t)m0 * NB, own0));
+        if (world > 1) SB_TRY(bcast_panel(c, f, k0, P1t, (size_t)tiled_panel_elems(m0), own0));
         markk(1);
         if (m0 <= 0) break;
-        SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k0 + 1, k0), f->L.ld(k0) * sizeof(double), Pc, m0 * sizeof(double),
-                                  m0 * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+        launch_untile_panel(P1t, 0, m0 / NB, f->L.blk(k0 + 1, k0), f->L.ld(k0), st);
         // second half panel: block column k1 gets the k0 update first, then is factored
         const int64_t m1 = m0 - NB;
-        double* P2 = Pc + (int64_t)NB * m0 + NB;  // column 128, row offset 128 (row 0 <-> block row k1)
         if (own1 == rank) {
-            launch_syrk_packed(f->L, k0, Pc, NB, k1, k1 + 1, rank, world, st);
+            launch_syrk_packed(f->L, k0, P1t, nullptr, NB, k1, k1 + 1, rank, world, st);
             launch_potrf_inv(f->L, k1, f->N, f->invL, f->logdet_blk, f->info_dev, st);
-            if (m1 > 0)
-                launch_gemm_nt(f->L.blk(k1 + 1, k1), f->L.ld(k1), f->invL + k1 * (int64_t)NB * NB, NB, P2, m0,
-                               m1, NB, NB, 1.0, 0.0, st);
+            if (m1 > 0)  // rows of P2t start at row block 1 (block row k1+1)
+                launch_trsm_tiled(f->L.blk(k1 + 1, k1), f->L.ld(k1), f->invL + k1 * (int64_t)NB * NB,
+                                  P2t + tiled_panel_elems(NB), m1, st);
         }
         markk(0);
-        if (world > 1) SB_TRY(bcast_panel(c, f, k1, Pc + (int64_t)NB * m0, m1 > 0 ? (size_t)m0 * NB : 0, own1));
+        if (world > 1) SB_TRY(bcast_panel(c, f, k1, P2t + tiled_panel_elems(NB), m1 > 0 ? (size_t)tiled_panel_elems(m1) : 0, own1));
         markk(1);
         if (m1 > 0) {
-            SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k1 + 1, k1), f->L.ld(k1) * sizeof(double), P2, m0 * sizeof(double),
-                                      m1 * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+            launch_untile_panel(P2t, 1, m1 / NB, f->L.blk(k1 + 1, k1), f->L.ld(k1), st);
             int64_t tiles = syrk_packed_tiles(nblk, k0, k1 + 1, nblk, rank, world);
             markk(0);
-            launch_syrk_packed(f->L, k0, Pc, 2 * NB, k1 + 1, nblk, rank, world, st);
+            launch_syrk_packed(f->L, k0, P1t, P2t, 2 * NB, k1 + 1, nblk, rank, world, st);
             markk(2);
             if (tiles > 0) {
                 flops += (double)tiles * 2.0 * NB * NB * (2.0 * NB);
@@ -654,7 +652,7 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
     f->bytes_L = (size_t)f->L.total() * sizeof(double);
     f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
     f->bytes_ld = (size_t)nblk * sizeof(double);
-    f->bytes_panel = (size_t)2 * f->Np * NB * sizeof(double);
+    f->bytes_panel = (size_t)2 * tiled_panel_elems(f->Np) * sizeof(double);
     f->bytes_alpha = (size_t)f->Np * sizeof(double);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->L.base, f->bytes_L);
@@ -725,7 +723,7 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
     f->bytes_L = (size_t)f->L.total() * sizeof(double);
     f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
     f->bytes_ld = (size_t)nblk * sizeof(double);
-    f->bytes_panel = (size_t)2 * f->Np * NB * sizeof(double);  // Np x 256 panel pair
+    f->bytes_panel = (size_t)2 * tiled_panel_elems(f->Np) * sizeof(double);  // two tiled half panels
     f->bytes_alpha = (size_t)f->Np * sizeof(double);
     SB_CUDA_F(c->pool_alloc((void**)&f->L.base, f->bytes_L));
     SB_CUDA_F(c->pool_alloc((void**)&f->invL, f->bytes_invL));

@@ -25,11 +25,17 @@ constexpr int KC = 16;   // k-slab per pipeline stage
 constexpr int STAGES = 4;
 constexpr int LDA_S = BM + 4;
 constexpr int LDB_S = BN + 4;
-constexpr int THREADS = 256;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * KC * (LDA_S + LDB_S) * 8 + 2 * STAGES * 8 + 8 * 128;
+constexpr int SLAB = KC * LDA_S;           // doubles in one A k-slab image  [16][132]
+constexpr int SLAB_BYTES = SLAB * 8;       // 16896
+constexpr int SLAB_B = KC * LDB_S;         // B stage [16][68]
+constexpr int MATH_WARPS = 8;
+constexpr int THREADS = (MATH_WARPS + 1) * 32;  // + 1 TMA producer warp
+constexpr size_t SMEM_BYTES = (size_t)STAGES * (SLAB + SLAB_B) * 8 + 2 * STAGES * 8 + 64;
 
 struct GemmArgs {
     int mode;  // 0 plain, 1 packed SYRK
+    int a_tiled, b_tiled, c_tiled;  // operand / output stored as k-slab images (see TILED below)
+    const double* A2;               // tiled SYRK: second half panel (k-chunks >= 8)
     const double* A;
     int64_t lda;
     const double* B;
@@ -84,11 +90,20 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
+// TILED layout of a panel (written by the TRSM epilogue, read by the SYRK): for every 128-row
+// block rb and panel column k (0..127) a padded column of 132 doubles; slab (rb, kc) = 16
+// consecutive padded columns = exactly the shared-memory image [16][132] of a k-slab, so the
+// TMA producer moves a whole operand slab with ONE bulk copy of 16896 bytes.
+//   addr(rb, k, r) = ((rb * 128 + k) * 132 + r)
 struct TilePtrs {
     const double* A;
     const double* B;
     double* C;
     int64_t lda, ldb, ldc;
+    int64_t a_blk, b_blk;  // tiled: 128-row block index of the operands
+    int b_row_off;         // tiled B: 0 or 64 (which half of the 128-row slab this tile uses)
+    int64_t c_rt;          // tiled C: row tile
+    int c_ct;              // tiled C: column tile (0/1)
 };
 
 // Walks the tiles blockIdx.x, +gridDim.x, ... of one launch.  Packed SYRK tiles are enumerated
@@ -124,6 +139,8 @@ struct TileCursor {
             p.A = g.A + rt * BM;
             p.B = g.B + ct * BN;
             p.C = g.C + ct * BN * g.ldc + rt * BM;
+            p.a_blk = rt; p.b_blk = ct >> 1; p.b_row_off = 0;
+            p.c_rt = rt; p.c_ct = (int)ct;
         } else {
             const int64_t loc = t - s0;
             const int64_t I = J + (loc >> 1);
@@ -134,6 +151,8 @@ struct TileCursor {
             p.B = g.A + (J - g.k - 1) * NB + h * BN;
             p.ldc = g.Pk.ld(J);
             p.C = g.Pk.blk(I, J) + (int64_t)h * BN * p.ldc;
+            p.a_blk = I - g.k - 1; p.b_blk = J - g.k - 1; p.b_row_off = h * BN;
+            p.c_rt = 0; p.c_ct = 0;
         }
         return p;
     }
@@ -143,16 +162,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Persistent CTAs (2 per SM): each walks tiles blockIdx.x, +gridDim.x, ...  The operand ring is
-// addressed by a chunk counter that runs ACROSS tiles, so the TMA engine is already filling the
-// next tile's first k-slabs while the warps are still in the current tile's epilogue.  No
-// CTA-wide barrier in the steady state: full[] (TMA -> warps, tx-count) and empty[] (8 warps ->
-// producer lane) mbarriers only.
+// Persistent CTAs (2 per SM): each walks tiles blockIdx.x, +gridDim.x, ...  Warp-specialised:
+// warps 0..7 are math warps (LDS.64 fragments + DMMA + epilogue, no copy-issue code at all);
+// warp 8 is the TMA producer: its lane 0 runs the whole refill loop (wait empty[] -> proxy fence
+// -> arm full[] with the slab's byte count -> 32 bulk copies).  Issuing bulk copies from the math
+// warps cost 12 % of the tensor pipe (ablation in profiles/): a UBLKCP stalls its warp ~30 ns.
+// The ring is addressed by a chunk counter that runs ACROSS tiles, so the next tile's first
+// k-slabs are already landing while the math warps are in the current tile's epilogue.  No
+// CTA-wide barrier in steady state: full[] (tx-count) / empty[] (8 warp arrivals) mbarriers only.
 __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_constant__ GemmArgs g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
-    double* sB = sA + STAGES * KC * LDA_S;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * KC * LDB_S);
+    double* sB = sA + STAGES * SLAB;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * SLAB_B);
     uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -162,69 +184,67 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full[s], THREADS / 32);  // one arrive.expect_tx per issuing warp
-            mbar_init(&empty[s], THREADS / 32);
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], MATH_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    // ---- distributed producer: lane 0 of EVERY warp issues its 4 of the 32 bulk copies of a
-    // k-slab (a bulk copy costs its issuing thread ~30 ns -- tools/mb_bulk.cu -- so one lane
-    // issuing all 32 sat on warp 0's critical path).  Lane 0 of warp 0 additionally arms the
-    // slab's mbarrier with the byte count.  Each warp tracks the producer cursor redundantly
-    // (identical values in all warps), in registers of lane 0 only via a small shared struct.
-    struct ProducerState {
-        TileCursor cur;
-        TilePtrs pp;
-        int pc, pslot;
-        uint32_t pphase;  // parity to wait for on empty[pslot] before refilling it
-        int pfirst;       // first pass over the ring: slots are fresh, no wait
-        int pdone;
-    };
-    ProducerState* ps = reinterpret_cast<ProducerState*>(empty + STAGES) + warp;
-    auto issue_next = [&]() {  // lane 0 of each warp
-        ProducerState st = *ps;
-        if (!st.pfirst) mbar_wait(&empty[st.pslot], st.pphase);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full[st.pslot], (BM + BN) * 2 * 8);  // this warp's 2 + 2 columns
-        const double* srcA = st.pp.A + ((int64_t)st.pc * KC + warp * 2) * st.pp.lda;
-        const double* srcB = st.pp.B + ((int64_t)st.pc * KC + warp * 2) * st.pp.ldb;
-        double* dA = sA + (st.pslot * KC + warp * 2) * LDA_S;
-        double* dB = sB + (st.pslot * KC + warp * 2) * LDB_S;
+    if (warp == MATH_WARPS) {
+        // ================= TMA producer warp =================
+        if (lane == 0) {
+            TileCursor pcur;
+            pcur.init(g, blockIdx.x);
+            int pslot = 0;
+            uint32_t pphase = 0;
+            bool pfirst = true;  // first pass over the ring: slots are fresh, nothing to wait for
+            for (; pcur.t < g.total_tiles; pcur.advance(g, gridDim.x)) {
+                const TilePtrs pp = pcur.ptrs(g);
+                for (int pc = 0; pc < nchunks; pc++) {
+                    if (!pfirst) {
+                        mbar_wait(&empty[pslot], pphase);
+                        // generic-proxy reads of the slot (math warps) -> async-proxy refill
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    const uint32_t abytes = g.a_tiled ? SLAB_BYTES : BM * KC * 8;
+                    mbar_expect_tx(&full[pslot], abytes + BN * KC * 8);
+                    double* dA = sA + pslot * SLAB;
+                    double* dB = sB + pslot * SLAB_B;
+                    const bool second = (pc >= 8 && g.A2 != nullptr);
+                    if (g.a_tiled) {  // one bulk copy: the slab is stored as its shared-memory image
+                        const double* base = second ? g.A2 : g.A;
+                        bulk_g2s(dA, base + (pp.a_blk * 128 + (pc & 7) * KC) * LDA_S, SLAB_BYTES, &full[pslot]);
+                    } else {
+                        const double* srcA = pp.A + (int64_t)pc * KC * pp.lda;
 #pragma unroll
-        for (int kk = 0; kk < 2; kk++) {
-            bulk_g2s(dA + kk * LDA_S, srcA + kk * st.pp.lda, BM * 8, &full[st.pslot]);
-            bulk_g2s(dB + kk * LDB_S, srcB + kk * st.pp.ldb, BN * 8, &full[st.pslot]);
+                        for (int kk = 0; kk < KC; kk++) bulk_g2s(dA + kk * LDA_S, srcA + kk * pp.lda, BM * 8, &full[pslot]);
+                    }
+                    {   // B: 16 half-columns of 64 rows (from a column-major matrix, or strided out of
+                        // the tiled panel: same bytes as needed, no over-fetch)
+                        const double* srcB = g.b_tiled
+                            ? (second ? g.A2 : g.A) + (pp.b_blk * 128 + (pc & 7) * KC) * LDA_S + pp.b_row_off
+                            : pp.B + (int64_t)pc * KC * pp.ldb;
+                        const int64_t ldb = g.b_tiled ? (int64_t)LDA_S : pp.ldb;
+#pragma unroll
+                        for (int kk = 0; kk < KC; kk++) bulk_g2s(dB + kk * LDB_S, srcB + kk * ldb, BN * 8, &full[pslot]);
+                    }
+                    if (++pslot == STAGES) {
+                        pslot = 0;
+                        if (pfirst) pfirst = false; else pphase ^= 1;
+                    }
+                }
+            }
         }
-        if (++st.pslot == STAGES) {
-            st.pslot = 0;
-            if (st.pfirst) st.pfirst = 0; else st.pphase ^= 1;
-        }
-        if (++st.pc == nchunks) {
-            st.pc = 0;
-            st.cur.advance(g, gridDim.x);
-            st.pdone = st.cur.t >= g.total_tiles;
-            if (!st.pdone) st.pp = st.cur.ptrs(g);
-        }
-        *ps = st;
-    };
-    const bool producer = (lane == 0);
-    if (producer) {
-        ProducerState st;
-        st.cur.init(g, blockIdx.x);
-        st.pc = 0; st.pslot = 0; st.pphase = 0; st.pfirst = 1;
-        st.pdone = st.cur.t >= g.total_tiles;
-        if (!st.pdone) st.pp = st.cur.ptrs(g);
-        *ps = st;
-        for (int c = 0; c < STAGES - 1 && !ps->pdone; c++) issue_next();
+        return;
     }
 
+    // ================= math warps =================
     const int wr = warp & 3, wc = warp >> 2;  // 4 warps along rows, 2 along cols; 32x32 each
     const double alpha = g.alpha, beta = g.beta;
     const double* a_base = sA + wr * 32 + gid + tig * LDA_S;
-    const double* b_base = sB + wc * 32 + gid + tig * LDB_S;
+    const double* b_base0 = sB + wc * 32 + gid + tig * LDB_S;
     int slot = 0;
     uint32_t phase = 0;
     TileCursor cur;
@@ -236,13 +256,12 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
 #pragma unroll
             for (int i = 0; i < 4; i++) acc[j][i][0] = acc[j][i][1] = 0.0;
 
+        const TilePtrs tp = cur.ptrs(g);
+        const double* b_base = b_base0;
         for (int c = 0; c < nchunks; c++) {
-            // keep the ring STAGES-1 slabs ahead: refill the slot released by the previous chunk
-            if (producer && !ps->pdone) issue_next();
-            __syncwarp();
             mbar_wait(&full[slot], phase);
-            const double* a = a_base + slot * KC * LDA_S;
-            const double* b = b_base + slot * KC * LDB_S;
+            const double* a = a_base + slot * SLAB;
+            const double* b = b_base + slot * SLAB_B;
 #pragma unroll
             for (int k4 = 0; k4 < KC / 4; k4++) {
                 double rf[4], cf[4];
@@ -261,9 +280,12 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
         }
 
         // epilogue: thread owns rows (2*tig, 2*tig+1) of column gid in each 8x8 fragment
-        TilePtrs tp = cur.ptrs(g);
-        double* cbase = tp.C + (int64_t)(wc * 32 + gid) * tp.ldc + wr * 32 + 2 * tig;
-        const int64_t ldc = tp.ldc;
+        // tiled output (TRSM -> panel in slab-image layout): column k of row tile rt is the padded
+        // 132-double column ((rt*128 + k) * 132); this tile covers k = ct*64 .. ct*64+63
+        double* cbase = g.c_tiled
+            ? g.C + ((tp.c_rt * 128 + tp.c_ct * BN + wc * 32 + gid) * (int64_t)LDA_S) + wr * 32 + 2 * tig
+            : tp.C + (int64_t)(wc * 32 + gid) * tp.ldc + wr * 32 + 2 * tig;
+        const int64_t ldc = g.c_tiled ? (int64_t)LDA_S : tp.ldc;
         if (beta != 0.0) {
 #pragma unroll
             for (int jh = 0; jh < 2; jh++) {  // 8 x 16-byte loads in flight per thread
@@ -312,6 +334,12 @@ void ensure_attr() {
 
 }  // namespace
 
+static void launch_common(GemmArgs& g, cudaStream_t s) {
+    int64_t grid = g.total_tiles < 2 * g_num_sms ? g.total_tiles : 2 * g_num_sms;
+    gemm_nt_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g);
+    g_launch_count++;
+}
+
 void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                     int64_t ldc, int64_t M, int64_t Ncols, int64_t K, double alpha, double beta,
                     cudaStream_t s) {
@@ -322,11 +350,23 @@ void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, 
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.mtiles = M / BM;
     g.K = K; g.alpha = alpha; g.beta = beta;
-    int64_t tiles = (M / BM) * (Ncols / BN);
-    g.total_tiles = tiles;
-    int64_t grid = tiles < 2 * g_num_sms ? tiles : 2 * g_num_sms;
-    gemm_nt_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g);
-    g_launch_count++;
+    g.total_tiles = (M / BM) * (Ncols / BN);
+    launch_common(g, s);
+}
+
+// panel TRSM as a product with the explicit inverse: Pt (tiled, see TilePtrs) = A * invL^T,
+// A = m x 128 column-major (lda), invL = 128 x 128 column-major (ld 128)
+void launch_trsm_tiled(const double* A, int64_t lda, const double* invL, double* Pt, int64_t m,
+                       cudaStream_t s) {
+    if (m <= 0) return;
+    ensure_attr();
+    GemmArgs g{};
+    g.mode = 0;
+    g.A = A; g.lda = lda; g.B = invL; g.ldb = NB; g.C = Pt; g.ldc = 0; g.c_tiled = 1;
+    g.mtiles = m / BM;
+    g.K = NB; g.alpha = 1.0; g.beta = 0.0;
+    g.total_tiles = (m / BM) * (NB / BN);
+    launch_common(g, s);
 }
 
 int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int rank, int world) {
@@ -338,8 +378,10 @@ int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int
     return tiles;
 }
 
-void launch_syrk_packed(Packed Apk, int64_t k, const double* P, int64_t K, int64_t jlo, int64_t jhi,
-                        int rank, int world, cudaStream_t s) {
+// P1t / P2t: the two half panels in TILED layout; row block 0 <-> block row k+1 of the matrix
+// (P2t's first block is unused).  K = 128 uses P1t only, K = 256 both.
+void launch_syrk_packed(Packed Apk, int64_t k, const double* P1t, const double* P2t, int64_t K,
+                        int64_t jlo, int64_t jhi, int rank, int world, cudaStream_t s) {
     int64_t nblk = Apk.nblk();
     if (jlo < k + 1) jlo = k + 1;
     if (jhi > nblk) jhi = nblk;
@@ -349,13 +391,11 @@ void launch_syrk_packed(Packed Apk, int64_t k, const double* P, int64_t K, int64
     ensure_attr();
     GemmArgs g{};
     g.mode = 1;
-    g.A = P;
+    g.A = P1t; g.A2 = P2t; g.a_tiled = 1; g.b_tiled = 1;
     g.K = K; g.alpha = -1.0; g.beta = 1.0;
     g.Pk = Apk; g.k = k; g.J0 = J0; g.w = world;
     g.total_tiles = tiles * 2;
-    int64_t grid = g.total_tiles < 2 * g_num_sms ? g.total_tiles : 2 * g_num_sms;
-    gemm_nt_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g);
-    g_launch_count++;
+    launch_common(g, s);
 }
 
 }  // namespace sb

@@ -106,12 +106,20 @@ void launch_potrf_inv(Packed A, int64_t k, int64_t N, double* invL, double* logd
 void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                     int64_t ldc, int64_t M, int64_t Ncols, int64_t K, double alpha, double beta,
                     cudaStream_t s);
-// trailing update of the packed matrix with panel k held in P (rows from k*NB, ld = ld(k)):
-//   A[I,J] -= P_I * P_J^T   for k < J <= I < nblk   restricted to block columns J with
-//   (J % world) == rank when world > 1, and J in [jlo, jhi).  P has K columns (NB, or 2*NB for
-//   the two-level panel) and leading dimension Np - (k+1)*NB; its row 0 is block row k+1.
-void launch_syrk_packed(Packed A, int64_t k, const double* P, int64_t K, int64_t jlo, int64_t jhi,
-                        int rank, int world, cudaStream_t s);
+// Panel TRSM writing the panel in TILED (k-slab image) layout: [row block][128 cols][132 padded
+// rows]; see gemm_nt.cu.  tiled_panel_elems(m) doubles per half panel.
+void launch_trsm_tiled(const double* A, int64_t lda, const double* invL, double* Pt, int64_t m,
+                       cudaStream_t s);
+inline int64_t tiled_panel_elems(int64_t m) { return (m / NB) * (int64_t)NB * (NB + 4); }
+// tiled panel -> column-major block column of the packed matrix (rows below the diagonal block)
+void launch_untile_panel(const double* Pt, int64_t row_blk0, int64_t nrow_blks, double* dst, int64_t ld,
+                         cudaStream_t s);
+// trailing update of the packed matrix with the (half) panels of outer step k in TILED layout:
+//   A[I,J] -= P_I * P_J^T   for k < J <= I < nblk, block columns J in [jlo, jhi) with
+//   (J % world) == rank.  K = 128: P1t only; K = 256: P1t and P2t.  Row block 0 of the tiled
+//   buffers <-> block row k+1.
+void launch_syrk_packed(Packed A, int64_t k, const double* P1t, const double* P2t, int64_t K,
+                        int64_t jlo, int64_t jhi, int rank, int world, cudaStream_t s);
 int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int rank, int world);
 
 // vector solves on the packed factor (S right-hand sides, column-major N x S with ld = Np)

@@ -241,7 +241,22 @@ pack_lower_kernel(Packed L, const double* __restrict__ D, int64_t ld, double shi
     *L.at(r, c) = v;
 }
 
+// dst[(c) * ld + rb*128 + r] = Pt[((row_blk0 + rb) * 128 + c) * 132 + r]
+__global__ void __launch_bounds__(128)
+untile_panel_kernel(const double* __restrict__ Pt, int64_t row_blk0, double* __restrict__ dst, int64_t ld) {
+    const int64_t rb = blockIdx.x;
+    const int c = blockIdx.y, r = threadIdx.x;
+    dst[(int64_t)c * ld + rb * NB + r] = Pt[((row_blk0 + rb) * NB + c) * (int64_t)(NB + 4) + r];
+}
+
 }  // namespace
+
+void launch_untile_panel(const double* Pt, int64_t row_blk0, int64_t nrow_blks, double* dst, int64_t ld,
+                         cudaStream_t st) {
+    if (nrow_blks <= 0) return;
+    untile_panel_kernel<<<dim3((unsigned)nrow_blks, NB), NB, 0, st>>>(Pt, row_blk0, dst, ld);
+    g_launch_count++;
+}
 
 void launch_rowscale(double* W, int64_t ld, int64_t rows, int64_t cols, const double* s, cudaStream_t st) {
     if (rows <= 0 || cols <= 0) return;
