@@ -2,8 +2,10 @@
 // inverse of the resulting triangle (used to turn the panel TRSM and every later block
 // triangular solve into tensor-core products) and the block's share of logdet.
 // Replaces the unblocked dpotf2 step inside LAPACK dpotrf (AbstractGPs
-// `cholesky(Symmetric(cov(fx)))`).  Latency-bound, one CTA; it is kept off
-// the critical path by look-ahead in the driver loop (api.cu).
+// `cholesky(Symmetric(cov(fx)))`).  Latency-bound, one CTA: it is the serial
+// critical path of the factorisation (and of the multi-GPU pipeline), so it is blocked by 8
+// columns: 16 outer steps (instead of 128) with rank-8 trailing updates from registers, and a
+// blocked triangular inverse (8x8 diagonal inverses + block back-substitution).
 #include "sb_common.cuh"
 
 namespace sb {
@@ -11,21 +13,24 @@ namespace {
 
 constexpr int LDS = NB + 4;
 constexpr int PT = 512;
-constexpr size_t POTRF_SMEM = (size_t)NB * LDS * 8 + NB * 8 + 16;
+constexpr int PB = 8;            // panel width inside the block
+constexpr int NPB = NB / PB;     // 16 panels
+constexpr size_t POTRF_SMEM = (size_t)NB * LDS * 8 + (size_t)NPB * PB * PB * 8 + (size_t)NB * PB * 8 + NB * 8 + 64;
 
 __global__ void __launch_bounds__(PT, 1)
 potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
                  double* __restrict__ logdet_blk, long long* __restrict__ info) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s = reinterpret_cast<double*>(smem_raw);   // s[c*LDS + r]
-    double* col = s + NB * LDS;                        // NB
-    int* bad = reinterpret_cast<int*>(col + NB);
+    double* s = reinterpret_cast<double*>(smem_raw);   // s[c*LDS + r]: the block, column-major
+    double* dinv = s + NB * LDS;                       // [NPB][PB*PB]: inverses of the 8x8 diagonal blocks (col-major)
+    double* ybuf = dinv + NPB * PB * PB;               // [PB][NB] staging for the inverse sweep
+    double* rdiag = ybuf + NB * PB;                    // [NB] reciprocals of the pivots
+    int* bad = reinterpret_cast<int*>(rdiag + NB);
 
     const int tid = threadIdx.x;
     double* Akk = A.blk(k, k);
     const int64_t ld = A.ld(k);
 
-    // load lower triangle (upper = 0)
     for (int idx = tid; idx < NB * NB; idx += PT) {
         int r = idx % NB, c = idx / NB;
         s[c * LDS + r] = (r >= c) ? Akk[(int64_t)c * ld + r] : 0.0;
@@ -33,33 +38,70 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
     if (tid == 0) *bad = 0;
     __syncthreads();
 
-    // ---- right-looking unblocked Cholesky --------------------------------------------------
-    const int ri = tid % NB, lg = tid / NB;  // row, column group (PT/NB = 4 groups)
-    for (int j = 0; j < NB; j++) {
-        double d = s[j * LDS + j];
-        __syncthreads();
-        if (!(d > 0.0)) {  // also catches NaN
-            if (tid == 0 && *bad == 0) *bad = j + 1;
-            d = 1.0;  // keep going with finite garbage; info reports the failure
-        }
-        double piv = sqrt(d);
-        if (tid == j) s[j * LDS + j] = piv;
-        if (tid > j && tid < NB) s[j * LDS + tid] /= piv;
-        __syncthreads();
-        if (ri > j) {
-            const double lij = s[j * LDS + ri];
-            int l = j + 1 + lg;
-            for (; l + 12 <= ri; l += 16) {  // 4 independent updates in flight
-                double a0 = s[j * LDS + l], a1 = s[j * LDS + l + 4], a2 = s[j * LDS + l + 8],
-                       a3 = s[j * LDS + l + 12];
-                double c0 = s[l * LDS + ri], c1 = s[(l + 4) * LDS + ri], c2 = s[(l + 8) * LDS + ri],
-                       c3 = s[(l + 12) * LDS + ri];
-                s[l * LDS + ri] = c0 - lij * a0;
-                s[(l + 4) * LDS + ri] = c1 - lij * a1;
-                s[(l + 8) * LDS + ri] = c2 - lij * a2;
-                s[(l + 12) * LDS + ri] = c3 - lij * a3;
+    // ================= blocked right-looking Cholesky =================
+    const int ri = tid % NB, lg = tid / NB;  // row, column group (4 groups)
+    for (int jb = 0; jb < NPB; jb++) {
+        const int j0 = jb * PB;
+        // (a1) 8x8 diagonal block, one thread, fully unrolled in registers
+        if (tid == 0) {
+            double d[PB][PB];
+#pragma unroll
+            for (int c = 0; c < PB; c++)
+#pragma unroll
+                for (int r = 0; r < PB; r++) d[r][c] = (r >= c) ? s[(j0 + c) * LDS + j0 + r] : 0.0;
+#pragma unroll
+            for (int c = 0; c < PB; c++) {
+                double piv = d[c][c];
+                if (!(piv > 0.0)) {  // also catches NaN
+                    if (*bad == 0) *bad = j0 + c + 1;
+                    piv = 1.0;       // keep going with finite garbage; info reports the failure
+                }
+                // one slow op (rsqrt) instead of sqrt + divide on the serial critical path
+                double rinv = rsqrt(piv), r = piv * rinv;
+                r = fma(fma(-r, r, piv), 0.5 * rinv, r);  // one Newton step: r is sqrt(piv) to < 1 ulp
+                rinv = fma(fma(-r, rinv, 1.0), rinv, rinv);  // Newton step for 1/r (no divide)
+                d[c][c] = r;
+                rdiag[j0 + c] = rinv;
+#pragma unroll
+                for (int i = c + 1; i < PB; i++) d[i][c] *= rinv;
+#pragma unroll
+                for (int l = c + 1; l < PB; l++)
+#pragma unroll
+                    for (int i = l; i < PB; i++) d[i][l] -= d[i][c] * d[l][c];
             }
-            for (; l <= ri; l += 4) s[l * LDS + ri] -= lij * s[j * LDS + l];
+#pragma unroll
+            for (int c = 0; c < PB; c++)
+#pragma unroll
+                for (int r = c; r < PB; r++) s[(j0 + c) * LDS + j0 + r] = d[r][c];
+        }
+        __syncthreads();
+        // (a2) rows below the diagonal block: x * L8^T = a  (forward substitution per row)
+        if (tid < NB && tid >= j0 + PB) {
+            double a[PB];
+#pragma unroll
+            for (int c = 0; c < PB; c++) a[c] = s[(j0 + c) * LDS + tid];
+#pragma unroll
+            for (int c = 0; c < PB; c++) {
+                double acc = a[c];
+#pragma unroll
+                for (int p = 0; p < c; p++) acc -= a[p] * s[(j0 + p) * LDS + j0 + c];
+                a[c] = acc * rdiag[j0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < PB; c++) s[(j0 + c) * LDS + tid] = a[c];
+        }
+        __syncthreads();
+        // (b) rank-8 update of the trailing triangle: A[i][l] -= sum_p L[i][j0+p] L[l][j0+p]
+        if (ri >= j0 + PB) {
+            double li[PB];
+#pragma unroll
+            for (int p = 0; p < PB; p++) li[p] = s[(j0 + p) * LDS + ri];
+            for (int l = j0 + PB + lg; l <= ri; l += PT / NB) {
+                double acc = s[l * LDS + ri];
+#pragma unroll
+                for (int p = 0; p < PB; p++) acc = fma(-li[p], s[(j0 + p) * LDS + l], acc);
+                s[l * LDS + ri] = acc;
+            }
         }
         __syncthreads();
     }
@@ -78,39 +120,76 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
             logdet_blk[k] = 2.0 * acc;
             if (*bad != 0) {
                 long long v = (long long)(k * NB + *bad);
-                // keep the FIRST failing pivot (smallest index); 0 means "ok so far"
-                long long old = *info;
+                long long old = *info;  // keep the FIRST failing pivot (smallest index); 0 = ok so far
                 if (old == 0 || v < old) *info = v;
             }
         }
     }
-    __syncthreads();
 
-    // ---- in-place inverse of the lower triangle (unblocked trtri, columns right to left) ----
-    // X[j][j] = 1/L[j][j];  X[i][j] = -X[j][j] * sum_{p=j+1..i} X[i][p] * L[p][j]
-    const int row = tid >> 2, part = tid & 3;
-    for (int j = NB - 1; j >= 0; j--) {
-        if (tid < NB) col[tid] = s[j * LDS + tid];  // original column j of L
-        __syncthreads();
-        double xjj = 1.0 / col[j];
-        double acc = 0.0;
-        if (row > j) {
-            double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            int p = j + 1 + part;
-            for (; p + 12 <= row; p += 16) {
-                b0 = fma(s[p * LDS + row], col[p], b0);
-                b1 = fma(s[(p + 4) * LDS + row], col[p + 4], b1);
-                b2 = fma(s[(p + 8) * LDS + row], col[p + 8], b2);
-                b3 = fma(s[(p + 12) * LDS + row], col[p + 12], b3);
+    // ================= blocked inverse of the lower triangle (in place) =================
+    // (1) inverses of the 16 diagonal 8x8 triangles, one thread each
+    if (tid < NPB) {
+        const int j0 = tid * PB;
+        double d[PB][PB], x[PB][PB];
+#pragma unroll
+        for (int c = 0; c < PB; c++)
+#pragma unroll
+            for (int r = 0; r < PB; r++) d[r][c] = (r >= c) ? s[(j0 + c) * LDS + j0 + r] : 0.0;
+#pragma unroll
+        for (int c = 0; c < PB; c++) {          // column c of the inverse: L x = e_c
+#pragma unroll
+            for (int r = 0; r < PB; r++) {
+                if (r < c) { x[r][c] = 0.0; continue; }
+                double acc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int p = 0; p < r; p++)
+                    if (p >= c) acc -= d[r][p] * x[p][c];
+                x[r][c] = acc * rdiag[j0 + r];
             }
-            for (; p <= row; p += 4) b0 = fma(s[p * LDS + row], col[p], b0);
-            acc = (b0 + b1) + (b2 + b3);
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (part == 0) {
-            if (row > j) s[j * LDS + row] = -xjj * acc;
-            if (row == j) s[j * LDS + j] = xjj;
+#pragma unroll
+        for (int c = 0; c < PB; c++)
+#pragma unroll
+            for (int r = 0; r < PB; r++) dinv[tid * PB * PB + c * PB + r] = x[r][c];
+    }
+    __syncthreads();
+    // (2) block columns right to left:  X[below, jb] = -X[below, below] * L[below, jb] * Dinv_jb
+    //     thread (row i, q): columns 2q, 2q+1 of the 8-wide block
+    const int q = tid / NB;
+    for (int jb = NPB - 1; jb >= 0; jb--) {
+        const int j0 = jb * PB;
+        // Y[i][c] = sum_{p = j0+8 .. i} X[i][p] * L[p][j0+c]
+        double y0 = 0.0, y1 = 0.0;
+        if (ri >= j0 + PB) {
+            const double* t0 = s + (j0 + 2 * q) * LDS;
+            const double* t1 = t0 + LDS;
+#pragma unroll 4
+            for (int p = j0 + PB; p <= ri; p++) {
+                double xv = s[p * LDS + ri];
+                y0 = fma(xv, t0[p], y0);
+                y1 = fma(xv, t1[p], y1);
+            }
+            ybuf[(2 * q) * NB + ri] = y0;
+            ybuf[(2 * q + 1) * NB + ri] = y1;
+        }
+        __syncthreads();  // all reads of the original L[:, jb] are done
+        // X[i][j0+c] = -sum_{p >= c} Y[i][p] * Dinv[p][c]   (Dinv lower triangular)
+        const double* di = dinv + jb * PB * PB;
+        if (ri >= j0 + PB) {
+            double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < PB; p++) {
+                double yv = ybuf[p * NB + ri];
+                z0 = fma(yv, di[(2 * q) * PB + p], z0);       // Dinv[p][2q] stored col-major: [c*PB + r]
+                z1 = fma(yv, di[(2 * q + 1) * PB + p], z1);
+            }
+            s[(j0 + 2 * q) * LDS + ri] = -z0;
+            s[(j0 + 2 * q + 1) * LDS + ri] = -z1;
+        } else if (ri >= j0 && ri < j0 + PB) {
+            // diagonal 8x8 block of the inverse
+            int r = ri - j0;
+            s[(j0 + 2 * q) * LDS + ri] = (r >= 2 * q) ? di[(2 * q) * PB + r] : 0.0;
+            s[(j0 + 2 * q + 1) * LDS + ri] = (r >= 2 * q + 1) ? di[(2 * q + 1) * PB + r] : 0.0;
         }
         __syncthreads();
     }
