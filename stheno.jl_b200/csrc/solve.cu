@@ -10,24 +10,26 @@ namespace {
 
 constexpr int MAXS = 8;  // right-hand sides processed per pass
 
-// b_k <- invL_kk * b_k   (or invL_kk^T * b_k); one CTA per right-hand side
-__global__ void __launch_bounds__(NB)
+// b_k <- invL_kk * b_k   (or invL_kk^T * b_k); one CTA per right-hand side, 4 lanes per row
+__global__ void __launch_bounds__(4 * NB)
 trsv_diag_kernel(const double* __restrict__ invLk, double* __restrict__ bk, int64_t ldb,
                  int transpose) {
     __shared__ double x[NB];
     double* b = bk + (int64_t)blockIdx.x * ldb;
-    const int i = threadIdx.x;
-    x[i] = b[i];
+    const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
+    if (threadIdx.x < NB) x[threadIdx.x] = b[threadIdx.x];
     __syncthreads();
     double acc = 0.0;
     if (!transpose) {
 #pragma unroll 8
-        for (int p = 0; p <= i; p++) acc = fma(invLk[p * NB + i], x[p], acc);
+        for (int p = part; p <= i; p += 4) acc = fma(invLk[p * NB + i], x[p], acc);
     } else {
 #pragma unroll 8
-        for (int p = i; p < NB; p++) acc = fma(invLk[i * NB + p], x[p], acc);
+        for (int p = i + part; p < NB; p += 4) acc = fma(invLk[i * NB + p], x[p], acc);
     }
-    b[i] = acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) b[i] = acc;
 }
 
 // rows below block k:  b[r] -= sum_c L[r, k*NB + c] * x_k[c]
@@ -285,7 +287,7 @@ void launch_pack_lower(Packed L, const double* D, int64_t ld, double shift, cuda
 
 void launch_trsv_diag(const double* invLk, double* bk, int64_t ldb, int S, bool transpose,
                       cudaStream_t s) {
-    trsv_diag_kernel<<<S, NB, 0, s>>>(invLk, bk, ldb, transpose ? 1 : 0);
+    trsv_diag_kernel<<<S, 4 * NB, 0, s>>>(invLk, bk, ldb, transpose ? 1 : 0);
     g_launch_count++;
 }
 
