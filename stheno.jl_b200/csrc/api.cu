@@ -355,44 +355,39 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     auto markk = [&](int kind) { if (ft) { mark(); evkind.push_back(kind); } };
     double flops = 0;
     int64_t nlaunch = 0;
-    // two half panels in TILED layout (gemm_nt.cu); row block 0 <-> block row k0+1
-    double* P1t = f->panel;
-    double* P2t = f->panel + tiled_panel_elems(Np);
-    for (int64_t k0 = 0; k0 < nblk; k0 += 2) {
-        const int64_t k1 = k0 + 1;
-        const int64_t m0 = Np - (k0 + 1) * NB;
-        const int own0 = (int)(k0 % world), own1 = (int)(k1 % world);
-        markk(3);
-        if (own0 == rank) {
-            launch_potrf_inv(f->L, k0, f->N, f->invL, f->logdet_blk, f->info_dev, st);
-            if (m0 > 0)
-                launch_trsm_tiled(f->L.blk(k0 + 1, k0), f->L.ld(k0), f->invL + k0 * (int64_t)NB * NB, P1t, m0, st);
-        }
-        markk(0);
-        if (world > 1) SB_TRY(bcast_panel(c, f, k0, P1t, (size_t)tiled_panel_elems(m0), own0));
-        markk(1);
-        if (m0 <= 0) break;
-        launch_untile_panel(P1t, 0, m0 / NB, f->L.blk(k0 + 1, k0), f->L.ld(k0), st);
-        // second half panel: block column k1 gets the k0 update first, then is factored
-        const int64_t m1 = m0 - NB;
-        if (own1 == rank) {
-            launch_syrk_packed(f->L, k0, P1t, nullptr, NB, k1, k1 + 1, rank, world, st);
-            launch_potrf_inv(f->L, k1, f->N, f->invL, f->logdet_blk, f->info_dev, st);
-            if (m1 > 0)  // rows of P2t start at row block 1 (block row k1+1)
-                launch_trsm_tiled(f->L.blk(k1 + 1, k1), f->L.ld(k1), f->invL + k1 * (int64_t)NB * NB,
-                                  P2t + tiled_panel_elems(NB), m1, st);
-        }
-        markk(0);
-        if (world > 1) SB_TRY(bcast_panel(c, f, k1, P2t + tiled_panel_elems(NB), m1 > 0 ? (size_t)tiled_panel_elems(m1) : 0, own1));
-        markk(1);
-        if (m1 > 0) {
-            launch_untile_panel(P2t, 1, m1 / NB, f->L.blk(k1 + 1, k1), f->L.ld(k1), st);
-            int64_t tiles = syrk_packed_tiles(nblk, k0, k1 + 1, nblk, rank, world);
+    // the OUTER_BLOCKS panels of an outer step, each in TILED layout (gemm_nt.cu); row block 0 <->
+    // block row k0+1, panel q starts at row block q
+    const double* Pt[OUTER_BLOCKS];
+    double* Pw[OUTER_BLOCKS];
+    for (int q = 0; q < OUTER_BLOCKS; q++) Pt[q] = Pw[q] = f->panel + (int64_t)q * tiled_panel_elems(Np);
+    for (int64_t k0 = 0; k0 < nblk; k0 += OUTER_BLOCKS) {
+        const int nq = (int)(nblk - k0 < OUTER_BLOCKS ? nblk - k0 : OUTER_BLOCKS);
+        for (int q = 0; q < nq; q++) {
+            const int64_t kq = k0 + q;
+            const int64_t mq = Np - (kq + 1) * NB;  // rows below diagonal block kq
+            const int owner = (int)(kq % world);
+            double* Pq = Pw[q] + tiled_panel_elems((int64_t)q * NB);  // its first row block is block row kq+1
+            markk(3);
+            if (owner == rank) {
+                // bring block column kq up to date with the panels already factored in this outer step
+                if (q > 0) launch_syrk_packed(f->L, k0, Pt, q, kq, kq + 1, rank, world, st);
+                launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st);
+                if (mq > 0)
+                    launch_trsm_tiled(f->L.blk(kq + 1, kq), f->L.ld(kq), f->invL + kq * (int64_t)NB * NB, Pq, mq, st);
+            }
             markk(0);
-            launch_syrk_packed(f->L, k0, P1t, P2t, 2 * NB, k1 + 1, nblk, rank, world, st);
+            if (world > 1) SB_TRY(bcast_panel(c, f, kq, Pq, mq > 0 ? (size_t)tiled_panel_elems(mq) : 0, owner));
+            markk(1);
+            if (mq > 0) launch_untile_panel(Pt[q], q, mq / NB, f->L.blk(kq + 1, kq), f->L.ld(kq), st);
+        }
+        const int64_t jt = k0 + nq;  // first trailing block column
+        if (jt < nblk) {
+            int64_t tiles = syrk_packed_tiles(nblk, k0, jt, nblk, rank, world);
+            markk(0);
+            launch_syrk_packed(f->L, k0, Pt, nq, jt, nblk, rank, world, st);
             markk(2);
             if (tiles > 0) {
-                flops += (double)tiles * 2.0 * NB * NB * (2.0 * NB);
+                flops += (double)tiles * 2.0 * NB * NB * ((double)nq * NB);
                 nlaunch++;
             }
         }
@@ -652,7 +647,7 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
     f->bytes_L = (size_t)f->L.total() * sizeof(double);
     f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
     f->bytes_ld = (size_t)nblk * sizeof(double);
-    f->bytes_panel = (size_t)2 * tiled_panel_elems(f->Np) * sizeof(double);
+    f->bytes_panel = (size_t)OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);
     f->bytes_alpha = (size_t)f->Np * sizeof(double);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->L.base, f->bytes_L);
@@ -723,7 +718,7 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
     f->bytes_L = (size_t)f->L.total() * sizeof(double);
     f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
     f->bytes_ld = (size_t)nblk * sizeof(double);
-    f->bytes_panel = (size_t)2 * tiled_panel_elems(f->Np) * sizeof(double);  // two tiled half panels
+    f->bytes_panel = (size_t)OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);  // tiled panels of an outer step
     f->bytes_alpha = (size_t)f->Np * sizeof(double);
     SB_CUDA_F(c->pool_alloc((void**)&f->L.base, f->bytes_L));
     SB_CUDA_F(c->pool_alloc((void**)&f->invL, f->bytes_invL));
@@ -844,18 +839,30 @@ int32_t sb_factor_alpha(sb_ctx* c, sb_factor* f, void* alpha_out) {
 // W <- W L^{-T} (rows_p x Np, ld rows_p): right-looking block forward substitution, tensor-core
 // products only.  keep: write the result back into W; acc != null: acc[r] += sum_c result[r,c]^2.
 static int32_t trsm_sweep(sb_ctx* c, sb_factor* f, double* W, int64_t rows_p, double* Xk, bool keep, double* acc) {
+    // Xk: rows_p x 256 workspace.  Two block columns per outer step so the big update runs at K = 256.
     const int64_t nblk = f->L.nblk(), Np = f->Np;
-    for (int64_t k = 0; k < nblk; k++) {
-        double* Wk = W + k * NB * rows_p;
-        launch_gemm_nt(Wk, rows_p, f->invL + k * (int64_t)NB * NB, NB, Xk, rows_p, rows_p, NB, NB, 1.0, 0.0,
-                       c->stream);
-        if (keep)
-            SB_CUDA(cudaMemcpyAsync(Wk, Xk, (size_t)rows_p * NB * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        if (acc) launch_rowsumsq_acc(Xk, rows_p, rows_p, NB, acc, c->stream);
-        int64_t m = Np - (k + 1) * NB;
-        if (m > 0)
-            launch_gemm_nt(Xk, rows_p, f->L.blk(k + 1, k), f->L.ld(k), W + (k + 1) * NB * rows_p, rows_p, rows_p, m,
-                           NB, -1.0, 1.0, c->stream);
+    double* X0 = Xk;
+    double* X1 = Xk + rows_p * NB;
+    for (int64_t k0 = 0; k0 < nblk; k0 += 2) {
+        const int64_t k1 = k0 + 1;
+        double* W0 = W + k0 * NB * rows_p;
+        launch_gemm_nt(W0, rows_p, f->invL + k0 * (int64_t)NB * NB, NB, X0, rows_p, rows_p, NB, NB, 1.0, 0.0, c->stream);
+        if (keep) SB_CUDA(cudaMemcpyAsync(W0, X0, (size_t)rows_p * NB * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (acc) launch_rowsumsq_acc(X0, rows_p, rows_p, NB, acc, c->stream);
+        if (k1 >= nblk) break;
+        double* W1 = W + k1 * NB * rows_p;
+        launch_gemm_nt(X0, rows_p, f->L.blk(k1, k0), f->L.ld(k0), W1, rows_p, rows_p, NB, NB, -1.0, 1.0, c->stream);
+        launch_gemm_nt(W1, rows_p, f->invL + k1 * (int64_t)NB * NB, NB, X1, rows_p, rows_p, NB, NB, 1.0, 0.0, c->stream);
+        if (keep) SB_CUDA(cudaMemcpyAsync(W1, X1, (size_t)rows_p * NB * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (acc) launch_rowsumsq_acc(X1, rows_p, rows_p, NB, acc, c->stream);
+        const int64_t m = Np - (k1 + 1) * NB;
+        if (m > 0) {
+            const double* As[2] = {X0, X1};
+            const int64_t las[2] = {rows_p, rows_p};
+            const double* Bs[2] = {f->L.blk(k1 + 1, k0), f->L.blk(k1 + 1, k1)};
+            const int64_t lbs[2] = {f->L.ld(k0), f->L.ld(k1)};
+            launch_gemm_nt_seg(2, As, las, Bs, lbs, W + (k1 + 1) * NB * rows_p, rows_p, rows_p, m, -1.0, 1.0, c->stream);
+        }
     }
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -915,25 +922,11 @@ static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
         }
     }
     if (need_var) {
-        SB_TRY(Xk.alloc((size_t)Nsp * NB * sizeof(double)));
+        SB_TRY(Xk.alloc((size_t)Nsp * 2 * NB * sizeof(double)));
         SB_TRY(acc.alloc(Nsp * sizeof(double)));
         SB_CUDA(cudaMemsetAsync(acc.p, 0, Nsp * sizeof(double), c->stream));
         // V^T = W L^{-T}: block forward substitution from the right, tensor-core products only
-        for (int64_t k = 0; k < nblk; k++) {
-            double* Wk = W.d() + k * NB * Nsp;
-            launch_gemm_nt(Wk, Nsp, f->invL + k * (int64_t)NB * NB, NB, Xk.d(), Nsp, Nsp, NB, NB, 1.0, 0.0,
-                           c->stream);
-            if (full_cov)
-                SB_CUDA(cudaMemcpyAsync(Wk, Xk.p, (size_t)Nsp * NB * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            else
-                launch_rowsumsq_acc(Xk.d(), Nsp, Nsp, NB, acc.d(), c->stream);
-            int64_t m = Np - (k + 1) * NB;
-            if (m > 0) {
-                launch_gemm_nt(Xk.d(), Nsp, f->L.blk(k + 1, k), f->L.ld(k), W.d() + (k + 1) * NB * Nsp, Nsp,
-                               Nsp, m, NB, -1.0, 1.0, c->stream);
-                c->tm.trailing_flops += 0;  // accounted under predict
-            }
-        }
+        SB_TRY(trsm_sweep(c, f, W.d(), Nsp, Xk.d(), /*keep=*/full_cov, full_cov ? nullptr : acc.d()));
         if (!full_cov) {
             SB_TRY(pd.alloc(Nsp * sizeof(double)));
             SB_CUDA(cudaMemsetAsync(pd.p, 0, Nsp * sizeof(double), c->stream));
@@ -1100,7 +1093,7 @@ int32_t sb_vfe_create(sb_ctx* c, const sb_covspec* uu, const sb_noise* noise_u, 
     VFE_TRY(ddt.alloc(round_up(N, NC) * sizeof(double)));
     VFE_TRY(W.alloc((size_t)NC * Mp * sizeof(double)));
     VFE_TRY(T.alloc((size_t)NC * Mp * sizeof(double)));
-    VFE_TRY(Xk.alloc((size_t)NC * NB * sizeof(double)));
+    VFE_TRY(Xk.alloc((size_t)NC * 2 * NB * sizeof(double)));
     VFE_TRY(D.alloc((size_t)Mp * Mp * sizeof(double)));
     VFE_TRY(vv.alloc((size_t)(Mp + 8) * sizeof(double)));
     VFE_TRY(fro.alloc((size_t)(nchunks_total + 1) * sizeof(double)));
@@ -1202,7 +1195,7 @@ int32_t sb_vfe_predict(sb_ctx* c, sb_vfe* v, const sb_covspec* cross, const sb_c
     if (var_out) {
         SB_CHECK(prior_diag && prior_diag->nrows == Ns, "prior diag spec required for var");
         SB_TRY(dp.build(prior_diag, c->stream, true));
-        SB_TRY(Xk.alloc((size_t)Nsp * NB * sizeof(double)));
+        SB_TRY(Xk.alloc((size_t)Nsp * 2 * NB * sizeof(double)));
         SB_TRY(acc1.alloc(Nsp * sizeof(double)));
         SB_TRY(acc2.alloc(Nsp * sizeof(double)));
         SB_TRY(pd.alloc(Nsp * sizeof(double)));

@@ -32,14 +32,20 @@ constexpr int MATH_WARPS = 8;
 constexpr int THREADS = (MATH_WARPS + 1) * 32;  // + 1 TMA producer warp
 constexpr size_t SMEM_BYTES = (size_t)STAGES * (SLAB + SLAB_B) * 8 + 2 * STAGES * 8 + 64;
 
+constexpr int MAX_SEG = 4;
+
+// Operands are K-segmented: k-chunks [seg*seg_chunks, (seg+1)*seg_chunks) of A (B) come from
+// Aseg[seg] (Bseg[seg]) with leading dimension lda_seg[seg] (ldb_seg[seg]).  This is how one
+// launch applies 2..4 panels at once (K = 256 / 512): each half panel / block column of L lives in
+// its own buffer.  Tiled operands (see TilePtrs) ignore the leading dimensions.
 struct GemmArgs {
     int mode;  // 0 plain, 1 packed SYRK
-    int a_tiled, b_tiled, c_tiled;  // operand / output stored as k-slab images (see TILED below)
-    const double* A2;               // tiled SYRK: second half panel (k-chunks >= 8)
-    const double* A;
-    int64_t lda;
-    const double* B;
-    int64_t ldb;
+    int a_tiled, b_tiled, c_tiled;
+    int seg_chunks;                 // k-chunks (of KC columns) per segment
+    const double* Aseg[MAX_SEG];
+    int64_t lda_seg[MAX_SEG];
+    const double* Bseg[MAX_SEG];
+    int64_t ldb_seg[MAX_SEG];
     double* C;
     int64_t ldc;
     int64_t mtiles;  // plain: number of row tiles
@@ -48,7 +54,7 @@ struct GemmArgs {
     double alpha, beta;
     // packed SYRK
     Packed Pk;
-    int64_t k;      // panel index
+    int64_t k;      // first block column of the outer step (tiled row block 0 <-> block row k+1)
     int64_t J0;     // first owned block column >= jlo
     int64_t w;      // column stride (world)
 };
@@ -96,12 +102,11 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // TMA producer moves a whole operand slab with ONE bulk copy of 16896 bytes.
 //   addr(rb, k, r) = ((rb * 128 + k) * 132 + r)
 struct TilePtrs {
-    const double* A;
-    const double* B;
     double* C;
-    int64_t lda, ldb, ldc;
-    int64_t a_blk, b_blk;  // tiled: 128-row block index of the operands
-    int b_row_off;         // tiled B: 0 or 64 (which half of the 128-row slab this tile uses)
+    int64_t ldc;
+    int64_t a_off, b_off;  // column-major operands: row offset (elements) of this tile's rows
+    int64_t a_blk, b_blk;  // tiled operands: 128-row block index
+    int b_row_off;         // tiled B: 0 or 64 (which half of the 128-row block)
     int64_t c_rt;          // tiled C: row tile
     int c_ct;              // tiled C: column tile (0/1)
 };
@@ -135,22 +140,19 @@ struct TileCursor {
         TilePtrs p;
         if (g.mode == 0) {
             int64_t rt = t % g.mtiles, ct = t / g.mtiles;
-            p.lda = g.lda; p.ldb = g.ldb; p.ldc = g.ldc;
-            p.A = g.A + rt * BM;
-            p.B = g.B + ct * BN;
+            p.ldc = g.ldc;
+            p.a_off = rt * BM;
+            p.b_off = ct * BN;
             p.C = g.C + ct * BN * g.ldc + rt * BM;
-            p.a_blk = rt; p.b_blk = ct >> 1; p.b_row_off = 0;
+            p.a_blk = rt; p.b_blk = ct >> 1; p.b_row_off = (int)(ct & 1) * BN;
             p.c_rt = rt; p.c_ct = (int)ct;
         } else {
             const int64_t loc = t - s0;
             const int64_t I = J + (loc >> 1);
             const int h = (int)(loc & 1);
-            const int64_t m = g.Pk.Np - (g.k + 1) * NB;  // panel rows below diagonal block k
-            p.lda = p.ldb = m;
-            p.A = g.A + (I - g.k - 1) * NB;
-            p.B = g.A + (J - g.k - 1) * NB + h * BN;
             p.ldc = g.Pk.ld(J);
             p.C = g.Pk.blk(I, J) + (int64_t)h * BN * p.ldc;
+            p.a_off = p.b_off = 0;
             p.a_blk = I - g.k - 1; p.b_blk = J - g.k - 1; p.b_row_off = h * BN;
             p.c_rt = 0; p.c_ct = 0;
         }
@@ -212,21 +214,21 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
                     mbar_expect_tx(&full[pslot], abytes + BN * KC * 8);
                     double* dA = sA + pslot * SLAB;
                     double* dB = sB + pslot * SLAB_B;
-                    const bool second = (pc >= 8 && g.A2 != nullptr);
+                    const int seg = pc / g.seg_chunks, lc = pc - seg * g.seg_chunks;  // segment, chunk in it
                     if (g.a_tiled) {  // one bulk copy: the slab is stored as its shared-memory image
-                        const double* base = second ? g.A2 : g.A;
-                        bulk_g2s(dA, base + (pp.a_blk * 128 + (pc & 7) * KC) * LDA_S, SLAB_BYTES, &full[pslot]);
+                        bulk_g2s(dA, g.Aseg[seg] + (pp.a_blk * 128 + lc * KC) * LDA_S, SLAB_BYTES, &full[pslot]);
                     } else {
-                        const double* srcA = pp.A + (int64_t)pc * KC * pp.lda;
+                        const int64_t lda = g.lda_seg[seg];
+                        const double* srcA = g.Aseg[seg] + pp.a_off + (int64_t)lc * KC * lda;
 #pragma unroll
-                        for (int kk = 0; kk < KC; kk++) bulk_g2s(dA + kk * LDA_S, srcA + kk * pp.lda, BM * 8, &full[pslot]);
+                        for (int kk = 0; kk < KC; kk++) bulk_g2s(dA + kk * LDA_S, srcA + kk * lda, BM * 8, &full[pslot]);
                     }
                     {   // B: 16 half-columns of 64 rows (from a column-major matrix, or strided out of
                         // the tiled panel: same bytes as needed, no over-fetch)
+                        const int64_t ldb = g.b_tiled ? (int64_t)LDA_S : g.ldb_seg[seg];
                         const double* srcB = g.b_tiled
-                            ? (second ? g.A2 : g.A) + (pp.b_blk * 128 + (pc & 7) * KC) * LDA_S + pp.b_row_off
-                            : pp.B + (int64_t)pc * KC * pp.ldb;
-                        const int64_t ldb = g.b_tiled ? (int64_t)LDA_S : pp.ldb;
+                            ? g.Bseg[seg] + (pp.b_blk * 128 + lc * KC) * LDA_S + pp.b_row_off
+                            : g.Bseg[seg] + pp.b_off + (int64_t)lc * KC * ldb;
 #pragma unroll
                         for (int kk = 0; kk < KC; kk++) bulk_g2s(dB + kk * LDB_S, srcB + kk * ldb, BN * 8, &full[pslot]);
                     }
@@ -347,9 +349,27 @@ void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, 
     ensure_attr();
     GemmArgs g{};
     g.mode = 0;
-    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.Aseg[0] = A; g.lda_seg[0] = lda; g.Bseg[0] = B; g.ldb_seg[0] = ldb; g.C = C; g.ldc = ldc;
+    g.seg_chunks = (int)(K / KC);
     g.mtiles = M / BM;
     g.K = K; g.alpha = alpha; g.beta = beta;
+    g.total_tiles = (M / BM) * (Ncols / BN);
+    launch_common(g, s);
+}
+
+// C (M x Ncols) = beta*C + alpha * [A_0 A_1 ...] [B_0 B_1 ...]^T, every segment 128 columns wide
+void launch_gemm_nt_seg(int nseg, const double* const* A, const int64_t* lda, const double* const* B,
+                        const int64_t* ldb, double* C, int64_t ldc, int64_t M, int64_t Ncols, double alpha,
+                        double beta, cudaStream_t s) {
+    if (M <= 0 || Ncols <= 0 || nseg <= 0) return;
+    ensure_attr();
+    GemmArgs g{};
+    g.mode = 0;
+    for (int i = 0; i < nseg; i++) { g.Aseg[i] = A[i]; g.lda_seg[i] = lda[i]; g.Bseg[i] = B[i]; g.ldb_seg[i] = ldb[i]; }
+    g.C = C; g.ldc = ldc;
+    g.seg_chunks = NB / KC;
+    g.mtiles = M / BM;
+    g.K = (int64_t)nseg * NB; g.alpha = alpha; g.beta = beta;
     g.total_tiles = (M / BM) * (Ncols / BN);
     launch_common(g, s);
 }
@@ -362,7 +382,8 @@ void launch_trsm_tiled(const double* A, int64_t lda, const double* invL, double*
     ensure_attr();
     GemmArgs g{};
     g.mode = 0;
-    g.A = A; g.lda = lda; g.B = invL; g.ldb = NB; g.C = Pt; g.ldc = 0; g.c_tiled = 1;
+    g.Aseg[0] = A; g.lda_seg[0] = lda; g.Bseg[0] = invL; g.ldb_seg[0] = NB; g.C = Pt; g.ldc = 0; g.c_tiled = 1;
+    g.seg_chunks = NB / KC;
     g.mtiles = m / BM;
     g.K = NB; g.alpha = 1.0; g.beta = 0.0;
     g.total_tiles = (m / BM) * (NB / BN);
@@ -378,21 +399,23 @@ int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int
     return tiles;
 }
 
-// P1t / P2t: the two half panels in TILED layout; row block 0 <-> block row k+1 of the matrix
-// (P2t's first block is unused).  K = 128 uses P1t only, K = 256 both.
-void launch_syrk_packed(Packed Apk, int64_t k, const double* P1t, const double* P2t, int64_t K,
-                        int64_t jlo, int64_t jhi, int rank, int world, cudaStream_t s) {
+// Pt[0..nseg): the panels of one outer step in TILED layout; row block 0 <-> block row k+1 of
+// the matrix (panel q's first q row blocks are unused).  K = 128 * nseg.
+void launch_syrk_packed(Packed Apk, int64_t k, const double* const* Pt, int nseg, int64_t jlo, int64_t jhi,
+                        int rank, int world, cudaStream_t s) {
     int64_t nblk = Apk.nblk();
     if (jlo < k + 1) jlo = k + 1;
     if (jhi > nblk) jhi = nblk;
     int64_t J0 = jlo + ((rank - jlo % world) % world + world) % world;
     int64_t tiles = syrk_packed_tiles(nblk, k, jlo, jhi, rank, world);
-    if (tiles <= 0) return;
+    if (tiles <= 0 || nseg <= 0) return;
     ensure_attr();
     GemmArgs g{};
     g.mode = 1;
-    g.A = P1t; g.A2 = P2t; g.a_tiled = 1; g.b_tiled = 1;
-    g.K = K; g.alpha = -1.0; g.beta = 1.0;
+    for (int i = 0; i < nseg; i++) { g.Aseg[i] = Pt[i]; g.Bseg[i] = Pt[i]; }
+    g.a_tiled = 1; g.b_tiled = 1;
+    g.seg_chunks = NB / KC;
+    g.K = (int64_t)nseg * NB; g.alpha = -1.0; g.beta = 1.0;
     g.Pk = Apk; g.k = k; g.J0 = J0; g.w = world;
     g.total_tiles = tiles * 2;
     launch_common(g, s);

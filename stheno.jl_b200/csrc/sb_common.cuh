@@ -114,12 +114,16 @@ inline int64_t tiled_panel_elems(int64_t m) { return (m / NB) * (int64_t)NB * (N
 // tiled panel -> column-major block column of the packed matrix (rows below the diagonal block)
 void launch_untile_panel(const double* Pt, int64_t row_blk0, int64_t nrow_blks, double* dst, int64_t ld,
                          cudaStream_t s);
-// trailing update of the packed matrix with the (half) panels of outer step k in TILED layout:
-//   A[I,J] -= P_I * P_J^T   for k < J <= I < nblk, block columns J in [jlo, jhi) with
-//   (J % world) == rank.  K = 128: P1t only; K = 256: P1t and P2t.  Row block 0 of the tiled
-//   buffers <-> block row k+1.
-void launch_syrk_packed(Packed A, int64_t k, const double* P1t, const double* P2t, int64_t K,
-                        int64_t jlo, int64_t jhi, int rank, int world, cudaStream_t s);
+// trailing update of the packed matrix with the nseg panels of the outer step starting at block
+// column k, all in TILED layout:  A[I,J] -= sum_q P_q,I * P_q,J^T   for block columns J in
+// [jlo, jhi) with (J % world) == rank, I >= J.  Row block 0 of the tiled buffers <-> block row k+1.
+constexpr int OUTER_BLOCKS = 4;  // block columns per outer step: trailing updates use K = 512
+void launch_syrk_packed(Packed A, int64_t k, const double* const* Pt, int nseg, int64_t jlo, int64_t jhi,
+                        int rank, int world, cudaStream_t s);
+// plain product with K-segmented operands (each segment 128 columns with its own base / ld)
+void launch_gemm_nt_seg(int nseg, const double* const* A, const int64_t* lda, const double* const* B,
+                        const int64_t* ldb, double* C, int64_t ldc, int64_t M, int64_t Ncols, double alpha,
+                        double beta, cudaStream_t s);
 int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int rank, int world);
 
 // vector solves on the packed factor (S right-hand sides, column-major N x S with ld = Np)
