@@ -194,6 +194,12 @@ int32_t sb_predict(sb_ctx* ctx, sb_factor* f, const sb_covspec* cross,
 int32_t sb_predict_cov(sb_ctx* ctx, sb_factor* f, const sb_covspec* cross,
                        const sb_covspec* prior_full, void* cov_out);
 int32_t sb_rand(sb_ctx* ctx, sb_factor* f, const void* z, int32_t S, void* out);
+/* sb_predict_factor replaces  cholesky(Symmetric(cov(f_post(x*, noise))))  -- what
+ * rand / logpdf of a POSTERIOR FiniteGP do (README.md:96, examples/process_decomposition/
+ * script.jl:36): the N* x N* posterior covariance  prior_full - V'V + noise  is formed and
+ * factorised on the device; the returned handle works with sb_rand / sb_logpdf / sb_factor_logdet. */
+int32_t sb_predict_factor(sb_ctx* ctx, sb_factor* f, const sb_covspec* cross, const sb_covspec* prior_full,
+                          const sb_noise* noise, sb_factor** out, int64_t* info);
 /* debug / parity: copy the lower-triangular factor out as a dense column-major N x N matrix */
 int32_t sb_factor_get_L(sb_ctx* ctx, sb_factor* f, void* L_out);
 

@@ -871,7 +871,8 @@ static int32_t trsm_sweep(sb_ctx* c, sb_factor* f, double* W, int64_t rows_p, do
 // shared body of sb_predict / sb_predict_cov
 static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
                             const sb_covspec* prior, bool full_cov, void* mean_out, void* var_out,
-                            void* cov_out) {
+                            void* cov_out, const sb_noise* post_noise = nullptr, sb_factor** fac_out = nullptr,
+                            int64_t* info = nullptr) {
     begin_call(c);
     int64_t before = g_launch_count;
     SB_CHECK(cross->ncols == f->N, "cross spec must be N* x N");
@@ -944,8 +945,27 @@ static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
             SB_CUDA(cudaMemsetAsync(Cm.p, 0, (size_t)Nsp * Nsp * sizeof(double), c->stream));
             SB_TRY(assemble_dense(c, dp, Cm.d(), Nsp));
             launch_gemm_nt(W.d(), Nsp, W.d(), Nsp, Cm.d(), Nsp, Nsp, Nsp, Np, -1.0, 1.0, c->stream);
-            SB_CUDA(cudaMemcpy2DAsync(cov_out, Ns * sizeof(double), Cm.p, Nsp * sizeof(double),
-                                      Ns * sizeof(double), Ns, cudaMemcpyDefault, c->stream));
+            if (cov_out)
+                SB_CUDA(cudaMemcpy2DAsync(cov_out, Ns * sizeof(double), Cm.p, Nsp * sizeof(double),
+                                          Ns * sizeof(double), Ns, cudaMemcpyDefault, c->stream));
+            if (fac_out) {
+                // posterior covariance (+ noise) -> packed layout -> Cholesky, all on device
+                sb_factor* fn = nullptr;
+                SB_TRY(factor_alloc(c, Ns, &fn));
+                DevBuf nd(c);
+                double s2 = post_noise ? post_noise->sigma2 : 0.0;
+                launch_pack_lower(fn->L, Cm.d(), Nsp, (post_noise && post_noise->diag) ? 0.0 : s2, c->stream);
+                if (post_noise && post_noise->diag) {
+                    int32_t st2 = nd.alloc(Ns * sizeof(double));
+                    if (st2 != SB_OK) { sb_factor_destroy(fn); return st2; }
+                    cudaMemcpyAsync(nd.p, post_noise->diag, Ns * sizeof(double), cudaMemcpyDefault, c->stream);
+                    launch_add_diag(fn->L, nd.d(), Ns, c->stream);
+                }
+                launch_fill_padding(fn->L, Ns, c->stream);
+                int32_t st2 = factor_finish(c, fn, info, /*force_local=*/true);
+                if (st2 != SB_OK) { sb_factor_destroy(fn); return st2; }
+                *fac_out = fn;
+            }
             SB_CUDA(cudaStreamSynchronize(c->stream));
         }
     }
@@ -980,6 +1000,14 @@ int32_t sb_predict_cov(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
                        const sb_covspec* prior_full, void* cov_out) {
     SB_CHECK(c && f && cross && prior_full && cov_out, "null argument");
     return predict_impl(c, f, cross, prior_full, true, nullptr, nullptr, cov_out);
+}
+
+int32_t sb_predict_factor(sb_ctx* c, sb_factor* f, const sb_covspec* cross, const sb_covspec* prior_full,
+                          const sb_noise* noise, sb_factor** out, int64_t* info) {
+    SB_CHECK(c && f && cross && prior_full && out, "null argument");
+    *out = nullptr;
+    if (info) *info = 0;
+    return predict_impl(c, f, cross, prior_full, true, nullptr, nullptr, nullptr, noise, out, info);
 }
 
 int32_t sb_rand(sb_ctx* c, sb_factor* f, const void* z, int32_t S, void* out) {

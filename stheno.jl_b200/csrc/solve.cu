@@ -251,7 +251,18 @@ untile_panel_kernel(const double* __restrict__ Pt, int64_t row_blk0, double* __r
     dst[(int64_t)c * ld + rb * NB + r] = Pt[((row_blk0 + rb) * NB + c) * (int64_t)(NB + 4) + r];
 }
 
+__global__ void add_diag_kernel(Packed L, const double* __restrict__ d, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) *L.at(i, i) += d[i];
+}
+
 }  // namespace
+
+void launch_add_diag(Packed L, const double* d, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, d, n);
+    g_launch_count++;
+}
 
 void launch_untile_panel(const double* Pt, int64_t row_blk0, int64_t nrow_blks, double* dst, int64_t ld,
                          cudaStream_t st) {

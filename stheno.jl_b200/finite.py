@@ -105,7 +105,20 @@ class FiniteGP:
     # -- exact factorisation of cov(fx) = cov(f, x) + Sigma_y (device) ----------------------
     def factor(self) -> _Factor:
         if self.post is not None:
-            raise NotImplementedError("factorising a posterior FiniteGP: use rand/marginals entry points")
+            if not isinstance(self.post, PosteriorGP):
+                raise NotImplementedError("joint sampling from an approximate (VFE) posterior is not on the B200 path yet")
+            if self._factor is None:
+                # cholesky(cov(f_post(x*, noise))): posterior covariance formed and factorised on device
+                post = self.post
+                ls = Lowered(post.prior, self.x)
+                cross, full = spec_dense(ls, post.lx), spec_dense(ls, ls)
+                ns = _noise_struct(self.noise, ls.n)
+                h, info = C.c_void_p(), C.c_int64(0)
+                st = _lib.load().sb_predict_factor(post.fac.ctx.h, post.fac.h, C.byref(cross), C.byref(full),
+                                                   C.byref(ns), C.byref(h), C.byref(info))
+                _lib.check(st, info)
+                self._factor = _Factor(h, post.fac.ctx, ls.n)
+            return self._factor
         if self._factor is None:
             lx = self.lowered
             spec = spec_symmetric(lx)
@@ -200,6 +213,10 @@ def marginals(fx):
     return m, np.sqrt(v)
 
 
+def _finite_mean(fx):
+    return fx.post.mean(fx.x) if fx.post is not None else fx.lowered.mean()
+
+
 def logpdf(fx, y):
     """logpdf(fx, y) / logpdf(fx, Y) (columns of Y)."""
     if isinstance(fx, SparseFiniteGP):
@@ -207,12 +224,10 @@ def logpdf(fx, y):
         if Y.ndim == 2:
             return np.array([elbo(VFE(fx.finducing), fx.fobs, Y[:, j]) for j in range(Y.shape[1])])
         return elbo(VFE(fx.finducing), fx.fobs, Y)
-    if fx.post is not None:
-        raise NotImplementedError("logpdf of a posterior FiniteGP is not on the B200 path yet")
     Y = np.asarray(y, dtype=np.float64)
     if Y.shape[0] != len(fx):
         raise ValueError("length(y) != length(fx)")
-    m = fx.lowered.mean()
+    m = _finite_mean(fx)
     delta = np.asfortranarray(Y - (m if Y.ndim == 1 else m[:, None]))
     S = 1 if Y.ndim == 1 else Y.shape[1]
     fac = fx.factor()
@@ -227,16 +242,12 @@ def rand(fx, z):
     if isinstance(fx, SparseFiniteGP):
         return rand(fx.fobs, z)
     z = np.asarray(z, dtype=np.float64)
-    if fx.post is not None:
-        # posterior sampling: factorise the posterior covariance through the dense route
-        from scipy import linalg as _sla  # host Cholesky of an N* x N* matrix is NOT the hot path
-        raise NotImplementedError("joint posterior sampling is listed as 'next' (SURVEY.md 8f.2)")
     S = 1 if z.ndim == 1 else z.shape[1]
     zz = np.asfortranarray(z.reshape(len(fx), S))
     out = np.empty((len(fx), S), dtype=np.float64, order="F")
     fac = fx.factor()
     _lib.check(_lib.load().sb_rand(fac.ctx.h, fac.h, zz.ctypes.data, S, out.ctypes.data))
-    m = fx.lowered.mean()
+    m = _finite_mean(fx)
     return out[:, 0] + m if z.ndim == 1 else out + m[:, None]
 
 

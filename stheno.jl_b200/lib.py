@@ -55,7 +55,7 @@ EXPORTS = [
     "sb_ctx_destroy", "sb_ctx_timings", "sb_ctx_mark", "sb_ctx_elapsed_ms", "sb_owner_of_block",
     "sb_owned_trailing_tiles", "sb_row_chunk", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
     "sb_factor_destroy", "sb_factor_logdet", "sb_logpdf", "sb_factor_set_data", "sb_factor_alpha",
-    "sb_predict", "sb_predict_cov", "sb_rand", "sb_factor_get_L", "sb_vfe_create", "sb_vfe_predict",
+    "sb_predict", "sb_predict_cov", "sb_predict_factor", "sb_rand", "sb_factor_get_L", "sb_vfe_create", "sb_vfe_predict",
     "sb_vfe_destroy",
 ]
 
@@ -108,6 +108,7 @@ def load():
         "sb_factor_alpha": [vp, vp, vp],
         "sb_predict": [vp, vp, P(sb_covspec), P(sb_covspec), vp, vp],
         "sb_predict_cov": [vp, vp, P(sb_covspec), P(sb_covspec), vp],
+        "sb_predict_factor": [vp, vp, P(sb_covspec), P(sb_covspec), P(sb_noise), P(vp), P(i64)],
         "sb_rand": [vp, vp, vp, i32, vp],
         "sb_factor_get_L": [vp, vp, vp],
         "sb_vfe_create": [vp, P(sb_covspec), P(sb_noise), P(sb_covspec), P(sb_covspec), P(sb_noise), vp,

@@ -270,3 +270,24 @@ def test_config3_full_size_properties(sb):
     _residual_identity(sb, f, obs, y, dict(idx=idx, inputs=sub), 0.1)
     parts = sb.split(obs, y)
     assert [len(p) for p in parts] == [16384] * 3 and np.array_equal(parts[2], y[32768:])
+
+
+def test_posterior_finite_gp_rand_and_logpdf(sb, orc):
+    """rand / logpdf of a POSTERIOR FiniteGP (README.md:96, examples/process_decomposition/script.jl:36)."""
+    rng = np.random.default_rng(21)
+    fs, fo = both(sb, orc, f3_model)
+    x = rng.uniform(0, 10, 400)
+    y = rng.standard_normal(400)
+    names = ["f1", "f2", "f3"]
+    xs = [rng.uniform(0, 10, n) for n in (50, 37, 64)]
+    ps = sb.posterior(fs(sb.GPPPInput("f3", x), 0.1), y)
+    po = orc.posterior(fo(orc.GPPPInput("f3", x), 0.1), y)
+    bs = sb.BlockData(*[sb.GPPPInput(n, v) for n, v in zip(names, xs)])
+    bo = orc.BlockData(*[orc.GPPPInput(n, v) for n, v in zip(names, xs)])
+    Z = rng.standard_normal((151, 3))
+    for noise in (1e-6, rng.uniform(0.01, 0.02, 151)):
+        Ys, Yo = sb.rand(ps(bs, noise), Z), orc.rand(po(bo, noise), Z)
+        np.testing.assert_allclose(Ys, Yo, rtol=1e-7, atol=1e-8)
+        np.testing.assert_allclose(sb.logpdf(ps(bs, noise), Yo[:, 0]), orc.logpdf(po(bo, noise), Yo[:, 0]), rtol=1e-8)
+    f1, f2, f3 = sb.split(bs, Ys)
+    assert f1.shape == (50, 3) and f3.shape == (64, 3)
