@@ -97,12 +97,48 @@ __device__ __forceinline__ double eval_term(const TermDev& t, int64_t li, int64_
     return s * k;
 }
 
+__device__ __forceinline__ int64_t clampi(int64_t v, int64_t lo, int64_t hi) {
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// kappa for one (row pair) x (8 columns) strip of a 1-D term; KERNEL is uniform per term so the
+// dispatch happens once per term, not per element
+template <int KERNEL>
+__device__ __forceinline__ void strip_1d(const TermDev& t, double xa, double xb, double sa, double sb_,
+                                         const double* __restrict__ zr, const double* __restrict__ sr,
+                                         const int64_t (&lj)[8], double (&v)[8][2]) {
+    const double xa2 = __dmul_rn(xa, xa), xb2 = __dmul_rn(xb, xb);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const double y = zr[lj[j]];
+        const double scol = sr ? sr[lj[j]] : 1.0;
+        double ka, kb;
+        if (KERNEL == SB_K_WHITE) {
+            ka = (xa == y) ? 1.0 : 0.0;
+            kb = (xb == y) ? 1.0 : 0.0;
+        } else if (KERNEL == SB_K_CONST) {
+            ka = kb = t.param;
+        } else {
+            // Distances.jl GEMM-trick rounding sequence, op for op (no FMA contraction)
+            const double y2 = __dmul_rn(y, y);
+            const double da = fmax(__dsub_rn(__dadd_rn(xa2, y2), __dmul_rn(2.0, __dmul_rn(xa, y))), 0.0);
+            const double db = fmax(__dsub_rn(__dadd_rn(xb2, y2), __dmul_rn(2.0, __dmul_rn(xb, y))), 0.0);
+            ka = kappa(KERNEL, da, t.param);
+            kb = kappa(KERNEL, db, t.param);
+        }
+        v[j][0] = fma(sa * scol, ka, v[j][0]);
+        v[j][1] = fma(sb_ * scol, kb, v[j][1]);
+    }
+}
+
 // PACKED = true : write into the packed-lower matrix (skip tiles above the block diagonal,
 //                 add noise on the diagonal).
 // PACKED = false: write into a dense column-major matrix.
-template <bool PACKED>
+// ALL1D: every term has 1-D inputs (the common case): clamped, branch-free loads and one kernel
+//        dispatch per term; otherwise the generic per-element path.
+template <bool PACKED, bool ALL1D>
 __global__ void __launch_bounds__(256)
-assemble_kernel(BlockDev b, OutDense dense, Packed packed, int64_t N, double sigma2,
+assemble_kernel(const __grid_constant__ BlockDev b, OutDense dense, Packed packed, int64_t N, double sigma2,
                 const double* __restrict__ noise_diag) {
     const int64_t r_tile0 = (b.row0 / TR) * TR + (int64_t)blockIdx.x * TR;
     const int64_t c_tile0 = (b.col0 / TC) * TC + (int64_t)blockIdx.y * TC;
@@ -119,17 +155,38 @@ assemble_kernel(BlockDev b, OutDense dense, Packed packed, int64_t N, double sig
 #pragma unroll
     for (int j = 0; j < 8; j++) v[j][0] = v[j][1] = 0.0;
 
-    for (int ti = 0; ti < b.nterms; ti++) {
-        const TermDev& t = b.t[ti];
+    if (ALL1D) {
+        const int64_t la = clampi(r0 - b.row0, 0, b.nrows - 1), lb = clampi(r0 + 1 - b.row0, 0, b.nrows - 1);
+        int64_t lj[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int64_t c = c0 + j;
-            if (c < b.col0 || c >= cend) continue;
+        for (int j = 0; j < 8; j++) lj[j] = clampi(c0 + j - b.col0, 0, b.ncols - 1);
+        for (int ti = 0; ti < b.nterms; ti++) {
+            const TermDev& t = b.t[ti];
+            const double xa = t.zl[la], xb = t.zl[lb];
+            const double sa = t.sl ? t.coeff * t.sl[la] : t.coeff;
+            const double sb_ = t.sl ? t.coeff * t.sl[lb] : t.coeff;
+            switch (t.kernel) {
+                case SB_K_SE: strip_1d<SB_K_SE>(t, xa, xb, sa, sb_, t.zr, t.sr, lj, v); break;
+                case SB_K_MATERN12: strip_1d<SB_K_MATERN12>(t, xa, xb, sa, sb_, t.zr, t.sr, lj, v); break;
+                case SB_K_MATERN32: strip_1d<SB_K_MATERN32>(t, xa, xb, sa, sb_, t.zr, t.sr, lj, v); break;
+                case SB_K_MATERN52: strip_1d<SB_K_MATERN52>(t, xa, xb, sa, sb_, t.zr, t.sr, lj, v); break;
+                case SB_K_WHITE: strip_1d<SB_K_WHITE>(t, xa, xb, sa, sb_, t.zr, t.sr, lj, v); break;
+                default: strip_1d<SB_K_CONST>(t, xa, xb, sa, sb_, t.zr, t.sr, lj, v); break;
+            }
+        }
+    } else {
+        for (int ti = 0; ti < b.nterms; ti++) {
+            const TermDev& t = b.t[ti];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                int64_t r = r0 + i;
-                if (r < b.row0 || r >= rend) continue;
-                v[j][i] += eval_term<true>(t, r - b.row0, c - b.col0);
+            for (int j = 0; j < 8; j++) {
+                int64_t c = c0 + j;
+                if (c < b.col0 || c >= cend) continue;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    int64_t r = r0 + i;
+                    if (r < b.row0 || r >= rend) continue;
+                    v[j][i] += eval_term<true>(t, r - b.row0, c - b.col0);
+                }
             }
         }
     }
@@ -186,6 +243,12 @@ __global__ void assemble_diag_kernel(BlockDev b, double* __restrict__ out) {
         out[b.row0 + i] = v;
 }
 
+bool all_1d(const BlockDev& b) {
+    for (int t = 0; t < b.nterms; t++)
+        if (b.t[t].dim != 1) return false;
+    return true;
+}
+
 dim3 tile_grid(const BlockDev& b) {
     int64_t r_first = (b.row0 / TR) * TR, c_first = (b.col0 / TC) * TC;
     int64_t nrt = (b.row0 + b.nrows - r_first + TR - 1) / TR;
@@ -197,15 +260,20 @@ dim3 tile_grid(const BlockDev& b) {
 
 void launch_assemble_dense(const BlockDev& b, OutDense out, cudaStream_t s) {
     if (b.nrows == 0 || b.ncols == 0) return;
-    assemble_kernel<false><<<tile_grid(b), 256, 0, s>>>(b, out, Packed{nullptr, 0}, 0, 0.0, nullptr);
+    if (all_1d(b))
+        assemble_kernel<false, true><<<tile_grid(b), 256, 0, s>>>(b, out, Packed{nullptr, 0}, 0, 0.0, nullptr);
+    else
+        assemble_kernel<false, false><<<tile_grid(b), 256, 0, s>>>(b, out, Packed{nullptr, 0}, 0, 0.0, nullptr);
     g_launch_count++;
 }
 
 void launch_assemble_packed(const BlockDev& b, Packed out, int64_t N, double sigma2,
                             const double* noise_diag, cudaStream_t s) {
     if (b.nrows == 0 || b.ncols == 0) return;
-    assemble_kernel<true><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2,
-                                                       noise_diag);
+    if (all_1d(b))
+        assemble_kernel<true, true><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag);
+    else
+        assemble_kernel<true, false><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag);
     g_launch_count++;
 }
 
