@@ -337,9 +337,119 @@ static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, si
     return SB_OK;
 }
 
+// Multi-GPU factorisation with look-ahead.  Stream 1 (c->stream) runs the trailing updates,
+// stream 2 (c->stream2) the panel phases (column catch-up, potrf, TRSM, NCCL broadcast, untile).
+// The trailing update of outer step s is split into T^A (the 4 block columns that form the NEXT
+// step's panels; full grid) and T^B (everything to the right; persistent grid minus
+// LOOKAHEAD_SMS SMs).  Panel phase s+1 starts as soon as T^A_s is done and overlaps T^B_s, so the
+// serial potrf/TRSM/broadcast chain leaves the critical path.  Two sets of tiled panel buffers.
+constexpr int LOOKAHEAD_SMS = 8;
+
+static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* const* Pw, const double* const* Pt,
+                           int rank, int world, cudaStream_t st) {
+    const int64_t Np = f->Np;
+    for (int q = 0; q < nq; q++) {
+        const int64_t kq = k0 + q;
+        const int64_t mq = Np - (kq + 1) * NB;
+        const int owner = (int)(kq % world);
+        double* Pq = Pw[q] + tiled_panel_elems((int64_t)q * NB);
+        if (owner == rank) {
+            if (q > 0) launch_syrk_packed(f->L, k0, Pt, q, kq, kq + 1, rank, world, st);
+            launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st);
+            if (mq > 0)
+                launch_trsm_tiled(f->L.blk(kq + 1, kq), f->L.ld(kq), f->invL + kq * (int64_t)NB * NB, Pq, mq, st);
+        }
+        if (world > 1) {
+            SB_NCCL(nccl_dl::GroupStart());
+            SB_NCCL(nccl_dl::Broadcast(f->invL + kq * (int64_t)NB * NB, f->invL + kq * (int64_t)NB * NB,
+                                       (size_t)NB * NB, ncclDouble, owner, c->comm, st));
+            SB_NCCL(nccl_dl::Broadcast(f->logdet_blk + kq, f->logdet_blk + kq, 1, ncclDouble, owner, c->comm, st));
+            if (mq > 0)
+                SB_NCCL(nccl_dl::Broadcast(Pq, Pq, (size_t)tiled_panel_elems(mq), ncclDouble, owner, c->comm, st));
+            SB_NCCL(nccl_dl::GroupEnd());
+        }
+        if (mq > 0) launch_untile_panel(Pt[q], q, mq / NB, f->L.blk(kq + 1, kq), f->L.ld(kq), st);
+    }
+    return SB_OK;
+}
+
+static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f) {
+    const int64_t nblk = f->L.nblk(), Np = f->Np;
+    const int world = c->world, rank = c->rank;
+    cudaStream_t s1 = c->stream, s2 = c->stream2;
+    const int64_t nsteps = (nblk + OUTER_BLOCKS - 1) / OUTER_BLOCKS;
+    double* Pw[2][OUTER_BLOCKS];
+    const double* Pt[2][OUTER_BLOCKS];
+    for (int set = 0; set < 2; set++)
+        for (int q = 0; q < OUTER_BLOCKS; q++)
+            Pt[set][q] = Pw[set][q] = f->panel + (int64_t)(set * OUTER_BLOCKS + q) * tiled_panel_elems(Np);
+    std::vector<cudaEvent_t> ev_p(nsteps), ev_a(nsteps), ev_t0(nsteps), ev_t1(nsteps);
+    for (int64_t s = 0; s < nsteps; s++) {
+        ev_p[s] = c->next_event(); ev_a[s] = c->next_event(); ev_t0[s] = c->next_event(); ev_t1[s] = c->next_event();
+    }
+    cudaEvent_t e_start = c->next_event(), e_pend = c->next_event();
+    // stream 2 starts after everything already queued on stream 1 (assembly)
+    SB_CUDA(cudaEventRecord(e_start, s1));
+    SB_CUDA(cudaStreamWaitEvent(s2, e_start, 0));
+    {
+        const int nq0 = (int)(nblk < OUTER_BLOCKS ? nblk : OUTER_BLOCKS);
+        SB_TRY(panel_phase(c, f, 0, nq0, Pw[0], Pt[0], rank, world, s2));
+        SB_CUDA(cudaEventRecord(ev_p[0], s2));
+    }
+    double flops = 0;
+    int64_t nlaunch = 0;
+    for (int64_t s = 0; s < nsteps; s++) {
+        const int64_t k0 = s * OUTER_BLOCKS;
+        const int nq = (int)(nblk - k0 < OUTER_BLOCKS ? nblk - k0 : OUTER_BLOCKS);
+        const int set = (int)(s & 1);
+        const int64_t jt = k0 + nq;
+        SB_CUDA(cudaStreamWaitEvent(s1, ev_p[s], 0));
+        SB_CUDA(cudaEventRecord(ev_t0[s], s1));
+        if (jt < nblk) {
+            const int64_t jA = jt + OUTER_BLOCKS < nblk ? jt + OUTER_BLOCKS : nblk;
+            launch_syrk_packed(f->L, k0, Pt[set], nq, jt, jA, rank, world, s1);            // T^A: next panels' columns
+            SB_CUDA(cudaEventRecord(ev_a[s], s1));
+            if (s + 1 < nsteps) {
+                const int nq1 = (int)(nblk - jt < OUTER_BLOCKS ? nblk - jt : OUTER_BLOCKS);
+                SB_CUDA(cudaStreamWaitEvent(s2, ev_a[s], 0));
+                SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2));
+                SB_CUDA(cudaEventRecord(ev_p[s + 1], s2));
+            }
+            if (jA < nblk) launch_syrk_packed(f->L, k0, Pt[set], nq, jA, nblk, rank, world, s1, LOOKAHEAD_SMS);  // T^B
+            int64_t tiles = syrk_packed_tiles(nblk, k0, jt, nblk, rank, world);
+            if (tiles > 0) { flops += (double)tiles * 2.0 * NB * NB * ((double)nq * NB); nlaunch++; }
+        }
+        SB_CUDA(cudaEventRecord(ev_t1[s], s1));
+    }
+    SB_CUDA(cudaEventRecord(e_pend, s2));
+    SB_CUDA(cudaStreamWaitEvent(s1, e_pend, 0));
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(s1));
+    if (c->fine_timing) {
+        for (int64_t s = 0; s < nsteps; s++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_t0[s], ev_t1[s]);
+            c->tm.trailing_ms += ms;
+            c->tm.trailing_kernel_ms += ms;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e_start, ev_p[0]);
+        c->tm.panel_ms += ms;  // only the first, un-hidden panel phase is on the critical path
+    }
+    c->tm.trailing_flops += flops;
+    c->tm.trailing_launches += nlaunch;
+    return SB_OK;
+}
+
+static int32_t sync_diag_blocks_and_info(sb_ctx* c, sb_factor* f);
+
 int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     const int64_t nblk = f->L.nblk();
     const int world = force_local ? 1 : c->world, rank = force_local ? 0 : c->rank;
+    if (world > 1 && !getenv("SB_NO_LOOKAHEAD")) {
+        SB_TRY(cholesky_lookahead(c, f));
+        return sync_diag_blocks_and_info(c, f);
+    }
     const int64_t Np = f->Np;
     cudaStream_t st = c->stream;
     const bool ft = c->fine_timing;
@@ -392,7 +502,28 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
             }
         }
     }
-    if (world > 1) {
+    if (world > 1) SB_TRY(sync_diag_blocks_and_info(c, f));
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (ft) {
+        for (size_t i = 1; i < ev.size(); i++) {
+            if (evkind[i] == 3) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            if (evkind[i] == 0) c->tm.panel_ms += ms;
+            else if (evkind[i] == 1) c->tm.comm_ms += ms;
+            else { c->tm.trailing_ms += ms; c->tm.trailing_kernel_ms += ms; }
+        }
+    }
+    c->tm.trailing_flops += flops;
+    c->tm.trailing_launches += nlaunch;
+    return SB_OK;
+}
+
+static int32_t sync_diag_blocks_and_info(sb_ctx* c, sb_factor* f) {
+    const int64_t nblk = f->L.nblk();
+    const int world = c->world, rank = c->rank;
+    cudaStream_t st = c->stream;
         // the diagonal blocks themselves live only on their owners so far: share them so every
         // rank holds the complete factor (needed by the replicated / RHS-sharded solves)
         for (int64_t k = 0; k < nblk; k++) {
@@ -417,21 +548,7 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
         SB_CUDA(cudaStreamSynchronize(st));
         if (h == 0x7fffffffffffffffLL) h = 0;
         SB_CUDA(cudaMemcpyAsync(f->info_dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-    }
-    SB_CUDA(cudaGetLastError());
-    SB_CUDA(cudaStreamSynchronize(st));
-    if (ft) {
-        for (size_t i = 1; i < ev.size(); i++) {
-            if (evkind[i] == 3) continue;
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-            if (evkind[i] == 0) c->tm.panel_ms += ms;
-            else if (evkind[i] == 1) c->tm.comm_ms += ms;
-            else { c->tm.trailing_ms += ms; c->tm.trailing_kernel_ms += ms; }
-        }
-    }
-    c->tm.trailing_flops += flops;
-    c->tm.trailing_launches += nlaunch;
+        SB_CUDA(cudaStreamSynchronize(st));
     return SB_OK;
 }
 
@@ -647,7 +764,7 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
     f->bytes_L = (size_t)f->L.total() * sizeof(double);
     f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
     f->bytes_ld = (size_t)nblk * sizeof(double);
-    f->bytes_panel = (size_t)OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);
+    f->bytes_panel = (size_t)2 * OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);
     f->bytes_alpha = (size_t)f->Np * sizeof(double);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->L.base, f->bytes_L);
@@ -718,7 +835,7 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
     f->bytes_L = (size_t)f->L.total() * sizeof(double);
     f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
     f->bytes_ld = (size_t)nblk * sizeof(double);
-    f->bytes_panel = (size_t)OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);  // tiled panels of an outer step
+    f->bytes_panel = (size_t)2 * OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);  // 2 sets (look-ahead) of tiled panels
     f->bytes_alpha = (size_t)f->Np * sizeof(double);
     SB_CUDA_F(c->pool_alloc((void**)&f->L.base, f->bytes_L));
     SB_CUDA_F(c->pool_alloc((void**)&f->invL, f->bytes_invL));

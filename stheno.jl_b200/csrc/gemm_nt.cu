@@ -336,8 +336,10 @@ void ensure_attr() {
 
 }  // namespace
 
-static void launch_common(GemmArgs& g, cudaStream_t s) {
-    int64_t grid = g.total_tiles < 2 * g_num_sms ? g.total_tiles : 2 * g_num_sms;
+static void launch_common(GemmArgs& g, cudaStream_t s, int reserve_sms = 0) {
+    int64_t cap = 2 * (int64_t)(g_num_sms - reserve_sms);
+    if (cap < 2) cap = 2;
+    int64_t grid = g.total_tiles < cap ? g.total_tiles : cap;
     gemm_nt_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g);
     g_launch_count++;
 }
@@ -402,7 +404,7 @@ int64_t syrk_packed_tiles(int64_t nblk, int64_t k, int64_t jlo, int64_t jhi, int
 // Pt[0..nseg): the panels of one outer step in TILED layout; row block 0 <-> block row k+1 of
 // the matrix (panel q's first q row blocks are unused).  K = 128 * nseg.
 void launch_syrk_packed(Packed Apk, int64_t k, const double* const* Pt, int nseg, int64_t jlo, int64_t jhi,
-                        int rank, int world, cudaStream_t s) {
+                        int rank, int world, cudaStream_t s, int reserve_sms) {
     int64_t nblk = Apk.nblk();
     if (jlo < k + 1) jlo = k + 1;
     if (jhi > nblk) jhi = nblk;
@@ -418,7 +420,7 @@ void launch_syrk_packed(Packed Apk, int64_t k, const double* const* Pt, int nseg
     g.K = (int64_t)nseg * NB; g.alpha = -1.0; g.beta = 1.0;
     g.Pk = Apk; g.k = k; g.J0 = J0; g.w = world;
     g.total_tiles = tiles * 2;
-    launch_common(g, s);
+    launch_common(g, s, reserve_sms);
 }
 
 }  // namespace sb

@@ -118,8 +118,10 @@ void launch_untile_panel(const double* Pt, int64_t row_blk0, int64_t nrow_blks, 
 // column k, all in TILED layout:  A[I,J] -= sum_q P_q,I * P_q,J^T   for block columns J in
 // [jlo, jhi) with (J % world) == rank, I >= J.  Row block 0 of the tiled buffers <-> block row k+1.
 constexpr int OUTER_BLOCKS = 4;  // block columns per outer step: trailing updates use K = 512
+// reserve_sms > 0: the persistent grid leaves that many SMs free (look-ahead: the next panel
+// phase and its NCCL broadcast run there concurrently)
 void launch_syrk_packed(Packed A, int64_t k, const double* const* Pt, int nseg, int64_t jlo, int64_t jhi,
-                        int rank, int world, cudaStream_t s);
+                        int rank, int world, cudaStream_t s, int reserve_sms = 0);
 // plain product with K-segmented operands (each segment 128 columns with its own base / ld)
 void launch_gemm_nt_seg(int nseg, const double* const* A, const int64_t* lda, const double* const* B,
                         const int64_t* ldb, double* C, int64_t ldc, int64_t M, int64_t Ncols, double alpha,
