@@ -210,7 +210,7 @@ def gpu_main(args):
     ls = Lowered(f, sb.GPPPInput("f", xsd))
     spec_k, spec_c, spec_d = spec_symmetric(lx), spec_dense(ls, lx), spec_diag(ls)
     noise = sblib.sb_noise()
-    noise.sigma2, noise.diag = SIGMA2, None
+    noise.sigma2, noise.diag, noise.dense = SIGMA2, None, None
     lp_out = (C.c_double * 1)()
 
     call_s = {"factor": 0.0, "logpdf": 0.0, "set_data": 0.0, "predict": 0.0, "destroy": 0.0}

@@ -106,11 +106,15 @@ typedef struct {
     const sb_block* blocks;
 } sb_covspec;
 
-/* observation noise Sigma_y (AbstractGPs FiniteGP(f, x, sigma^2)): scalar -> sigma2*I,
- * diag != NULL -> Diagonal(diag).  Dense Sigma_y is "next" (SURVEY.md 8f). */
+/* observation noise Sigma_y (AbstractGPs FiniteGP(f, x, Sigma)): scalar -> sigma2*I;
+ * diag != NULL -> Diagonal(diag) (n values); dense != NULL -> full symmetric PSD matrix
+ * (n x n column-major, only its lower triangle is read), as exercised by
+ * test/affine_transformations/test_util.jl:114-127.  Exactly one form is used:
+ * dense, else diag, else scalar. */
 typedef struct {
     double sigma2;
-    const void* diag; /* NULL or n values */
+    const void* diag;  /* NULL or n values */
+    const void* dense; /* NULL or n*n values, column-major, leading dimension n */
 } sb_noise;
 
 typedef struct {

@@ -846,10 +846,14 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
     SB_CUDA_F(cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream));
     SB_CUDA_F(cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream));
 
-    DevBuf nd(c);
+    DevBuf nd(c), ndense(c);
     const double* noise_diag = nullptr;
     double sigma2 = 0.0;
-    if (noise) {
+    if (noise && noise->dense) {
+        SB_CHECK(f->N <= 65535, "dense observation noise: N <= 65535");
+        if (ndense.alloc((size_t)f->N * f->N * sizeof(double)) != SB_OK) return fail(SB_ERR_NOMEM);
+        SB_CUDA_F(cudaMemcpyAsync(ndense.p, noise->dense, (size_t)f->N * f->N * sizeof(double), cudaMemcpyDefault, c->stream));
+    } else if (noise) {
         sigma2 = noise->sigma2;
         if (noise->diag) {
             if (nd.alloc(f->N * sizeof(double)) != SB_OK) return fail(SB_ERR_NOMEM);
@@ -864,6 +868,7 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
             // the kernel skips foreign tiles via the ownership test below (single GPU: all).
             launch_assemble_packed(b, f->L, f->N, sigma2, noise_diag, c->stream);
         }
+        if (ndense.p) launch_add_dense_lower(f->L, ndense.d(), f->N, f->N, c->stream);
         launch_fill_padding(f->L, f->N, c->stream);
         t.stop();
         SB_CUDA_F(cudaGetLastError());
@@ -1192,6 +1197,7 @@ int32_t sb_vfe_create(sb_ctx* c, const sb_covspec* uu, const sb_noise* noise_u, 
     SB_CHECK(uu->nrows == M && uu->symmetric == 1, "uu must be the symmetric M x M spec of cov(fz)");
     SB_CHECK(ff_diag->nrows == N, "ff_diag must have N rows");
     SB_CHECK(N > 0 && M > 0, "empty problem");
+    SB_CHECK(noise_f->dense == nullptr, "VFE needs diagonal observation noise");
     cudaEvent_t t0 = c->next_event(), t1 = c->next_event();
     cudaEventRecord(t0, c->stream);
 

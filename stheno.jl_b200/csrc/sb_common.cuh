@@ -155,6 +155,7 @@ void launch_transpose(const double* in, int64_t ld_in, int64_t rows, int64_t col
                       int64_t ld_out, cudaStream_t st);
 void launch_pack_lower(Packed L, const double* D, int64_t ld, double shift, cudaStream_t st);
 void launch_add_diag(Packed L, const double* d, int64_t n, cudaStream_t st);
+void launch_add_dense_lower(Packed L, const double* D, int64_t ld, int64_t n, cudaStream_t st);
 
 extern thread_local int64_t g_launch_count;
 

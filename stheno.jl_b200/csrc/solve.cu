@@ -251,12 +251,27 @@ untile_panel_kernel(const double* __restrict__ Pt, int64_t row_blk0, double* __r
     dst[(int64_t)c * ld + rb * NB + r] = Pt[((row_blk0 + rb) * NB + c) * (int64_t)(NB + 4) + r];
 }
 
+// packed lower += dense symmetric matrix (n x n, ld), lower triangle only
+__global__ void __launch_bounds__(256)
+add_dense_lower_kernel(Packed L, const double* __restrict__ D, int64_t ld, int64_t n) {
+    int64_t c = blockIdx.y;
+    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= n || c >= n || r < c) return;
+    *L.at(r, c) += D[c * ld + r];
+}
+
 __global__ void add_diag_kernel(Packed L, const double* __restrict__ d, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) *L.at(i, i) += d[i];
 }
 
 }  // namespace
+
+void launch_add_dense_lower(Packed L, const double* D, int64_t ld, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    add_dense_lower_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, st>>>(L, D, ld, n);
+    g_launch_count++;
+}
 
 void launch_add_diag(Packed L, const double* d, int64_t n, cudaStream_t st) {
     if (n <= 0) return;

@@ -57,14 +57,21 @@ def _noise_struct(noise, n):
     if np.ndim(noise) == 0:
         ns.sigma2 = float(noise)
         ns.diag = None
+        ns.dense = None
     elif np.ndim(noise) == 1:
         keep = np.ascontiguousarray(noise, dtype=np.float64)
         if keep.shape[0] != n:
             raise ValueError("noise vector length mismatch")
         ns.sigma2 = 0.0
         ns.diag = keep.ctypes.data
+        ns.dense = None
     else:
-        raise NotImplementedError("dense observation-noise matrices are not on the B200 path yet")
+        keep = np.asfortranarray(noise, dtype=np.float64)
+        if keep.shape != (n, n):
+            raise ValueError("noise matrix shape mismatch")
+        ns.sigma2 = 0.0
+        ns.diag = None
+        ns.dense = keep.ctypes.data
     ns._keep = keep
     return ns
 

@@ -402,17 +402,29 @@ def extract_components(f: GPPP, x):
 
 @dataclass
 class LTerm:
-    atom: AtomicGP
+    atom: AtomicGP            # the leaf whose GP supplies the kernel
     coeff: float
     scale: np.ndarray | None  # per-point scale vector or None (== ones)
-    z: object  # inputs seen by the atom's kernel (1-D array or ColVecs)
+    z: object                 # inputs seen by the atom's kernel (1-D array or ColVecs)
+    key: tuple = ()           # identity of the leaf: ids of the chain of wrapping atomics (nested GPPPs)
+
+    def same_leaf(self, other) -> bool:
+        """Object identity as in src/gp/atomic_gp.jl:36-38; for a GPPP used as an atomic inside
+        another GPPP the whole chain of wrappers must coincide (two different outer atomics
+        wrapping the same inner programme are independent)."""
+        return self.atom is other.atom and self.key == other.key
 
 
 def lower(p: SthenoAbstractGP, x):
     """-> (mean vector, [LTerm]) of process p at inputs x."""
     if isinstance(p, AtomicGP):
         if isinstance(p.gp, GPPP):
-            raise NotImplementedError("nested GPPPs are not supported by the B200 path (v1)")
+            # a whole programme used as one atomic (test/gaussian_process_probabilistic_programme.jl:
+            # 107-120): its inputs are themselves GPPPInputs naming the inner process
+            if not isinstance(x, GPPPInput):
+                raise NotImplementedError("nested GPPP: only GPPPInput inner inputs are lowered (no BlockData / tuple vectors)")
+            m, terms = lower(p.gp.fs[x.p], x.x)
+            return m, [LTerm(t.atom, t.coeff, t.scale, t.z, (id(p),) + t.key) for t in terms]
         return p.gp.mean_vector(x), [LTerm(p, 1.0, None, x)]
     op = p.args[0]
     if op == "+":
@@ -429,10 +441,10 @@ def lower(p: SthenoAbstractGP, x):
         m, t = lower(p.args[2], x)
         if callable(s):
             sx = np.array([s(v) for v in iter_points(x)], dtype=np.float64)
-            out = [LTerm(u.atom, u.coeff, sx if u.scale is None else sx * u.scale, u.z) for u in t]
+            out = [LTerm(u.atom, u.coeff, sx if u.scale is None else sx * u.scale, u.z, u.key) for u in t]
             return sx * m, out
         s = float(s)
-        return s * m, [LTerm(u.atom, s * u.coeff, u.scale, u.z) for u in t]
+        return s * m, [LTerm(u.atom, s * u.coeff, u.scale, u.z, u.key) for u in t]
     if op == "o":
         return lower(p.args[1], map_input(p.args[2], x))
     if op == "cross":
@@ -496,7 +508,7 @@ class SpecBuilder:
         term0 = len(self.terms)
         for a in lt_rows:
             for b in lt_cols:
-                if a.atom is not b.atom:
+                if not a.same_leaf(b):
                     continue  # independent leaves: zeros (atomic_gp.jl:36-38)
                 for (kc, kid, param, iscale) in a.atom.gp.kernel.lowered():
                     zl = self._input(a.z, iscale)

@@ -29,7 +29,7 @@ struct SbCovSpec
     nrows::Int64; ncols::Int64; symmetric::Int32; narrays::Int32; arrays::Ptr{SbArray}
     nterms::Int32; terms::Ptr{SbTerm}; nblocks::Int32; blocks::Ptr{SbBlock}
 end
-struct SbNoise;  sigma2::Float64; diag::Ptr{Cvoid}; end
+struct SbNoise;  sigma2::Float64; diag::Ptr{Cvoid}; dense::Ptr{Cvoid}; end
 
 const K_SE, K_M12, K_M32, K_M52, K_WHITE, K_CONST = Int32.(0:5)
 
@@ -147,8 +147,8 @@ function factor(fx::B200Finite)
     ps, vs = components(fx.f, fx.x)
     spec, keep = build_spec(ps, vs, ps, vs; symmetric=true)
     Σ = fx.Σy
-    nd = Σ isa Diagonal ? collect(Float64, diag(Σ)) : error("SthenoB200: dense Σy not supported yet")
-    noise = SbNoise(0.0, pointer(nd))
+    nd = Σ isa Diagonal ? collect(Float64, diag(Σ)) : Matrix{Float64}(Σ)   # Diagonal or dense PSD Σy
+    noise = Σ isa Diagonal ? SbNoise(0.0, pointer(nd), C_NULL) : SbNoise(0.0, C_NULL, pointer(nd))
     h = Ref{Ptr{Cvoid}}(C_NULL); info = Ref{Int64}(0)
     GC.@preserve keep nd begin
         st = ccall((:sb_factor_create, LIB), Int32,
@@ -156,7 +156,7 @@ function factor(fx::B200Finite)
                    ctx().h, spec, noise, h, info)
     end
     check(st, info[])
-    F = Factor(h[], length(nd)); finalizer(destroy!, F); F
+    F = Factor(h[], length(fx.x)); finalizer(destroy!, F); F
 end
 
 function logpdf(fx::B200Finite, y::AbstractVector{<:Real})

@@ -36,7 +36,7 @@ class sb_covspec(C.Structure):
 
 
 class sb_noise(C.Structure):
-    _fields_ = [("sigma2", C.c_double), ("diag", C.c_void_p)]
+    _fields_ = [("sigma2", C.c_double), ("diag", C.c_void_p), ("dense", C.c_void_p)]
 
 
 class sb_timings(C.Structure):

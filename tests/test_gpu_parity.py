@@ -291,3 +291,40 @@ def test_posterior_finite_gp_rand_and_logpdf(sb, orc):
         np.testing.assert_allclose(sb.logpdf(ps(bs, noise), Yo[:, 0]), orc.logpdf(po(bo, noise), Yo[:, 0]), rtol=1e-8)
     f1, f2, f3 = sb.split(bs, Ys)
     assert f1.shape == (50, 3) and f3.shape == (64, 3)
+
+
+def test_dense_observation_noise(sb, orc):
+    """Dense PSD Sigma_y (test/affine_transformations/test_util.jl:114-120)."""
+    rng = np.random.default_rng(31)
+    n = 333
+    x = rng.uniform(0, 10, n)
+    A = rng.standard_normal((n, 5))
+    S = 0.05 * np.eye(n) + 0.02 * A @ A.T
+    y = rng.standard_normal(n)
+    fs, fo = both(sb, orc, toy_model)
+    fxs, fxo = fs(sb.GPPPInput("f3", x), S), fo(orc.GPPPInput("f3", x), S)
+    np.testing.assert_allclose(sb.logpdf(fxs, y), orc.logpdf(fxo, y), rtol=RTOL)
+    np.testing.assert_allclose(sb.cov(fxs), orc.cov(fxo), rtol=1e-13, atol=1e-14)
+    m, v = sb.mean_and_var(sb.posterior(fxs, y), sb.GPPPInput("f1", x[:40]))
+    mo, vo = orc.mean_and_var(orc.posterior(fxo, y), orc.GPPPInput("f1", x[:40]))
+    np.testing.assert_allclose(m, mo, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(v, vo, rtol=1e-9, atol=1e-10)
+
+
+def test_nested_gppp_on_device(sb, orc):
+    """A GPPP used as an atomic inside another GPPP (gppp.jl test :107-120), through the CUDA path."""
+    rng = np.random.default_rng(32)
+
+    def build(m):
+        inner = toy_model(m)
+        gpc = m.GPC()
+        f1 = m.atomic(inner, gpc)
+        return m.GPPP(dict(f1=f1, f2=5 * f1), gpc)
+
+    fs, fo = build(sb), build(orc)
+    x0, x1 = rng.standard_normal(50), rng.standard_normal(40)
+    a_s, b_s = sb.GPPPInput("f1", sb.GPPPInput("f3", x0)), sb.GPPPInput("f2", sb.GPPPInput("f1", x1))
+    a_o, b_o = orc.GPPPInput("f1", orc.GPPPInput("f3", x0)), orc.GPPPInput("f2", orc.GPPPInput("f1", x1))
+    np.testing.assert_allclose(sb.cov(fs, a_s, b_s), orc.cov(fo, a_o, b_o), rtol=1e-13, atol=1e-14)
+    y = rng.standard_normal(50)
+    np.testing.assert_allclose(sb.logpdf(fs(a_s, 0.1), y), orc.logpdf(fo(a_o, 0.1), y), rtol=RTOL)

@@ -86,3 +86,31 @@ def test_errors_match_reference(sb):
     assert a.n == 1 and gpc1.n == 1
     c = 2 * a + 1.0
     assert c.n == 3 and gpc1.n == 3                     # unnamed intermediates still get ids
+
+
+def test_nested_gppp_lowering(sb, orc):
+    """test/gaussian_process_probabilistic_programme.jl:107-120: a GPPP used as an atomic inside
+    another GPPP; inputs GPPPInput(:f1, GPPPInput(:f1, x))."""
+    from stheno_jl_b200.gp import Lowered, spec_dense, spec_diag
+    rng = np.random.default_rng(13)
+
+    def build(m):
+        inner = toy_model(m)
+        gpc = m.GPC()
+        f1 = m.atomic(inner, gpc)
+        f3 = m.atomic(inner, gpc)            # a second, independent wrapper of the same programme
+        return m.GPPP(dict(f1=f1, f2=5 * f1, f3=f3), gpc)
+
+    fs, fo = build(sb), build(orc)
+    x0, x1 = rng.standard_normal(5), rng.standard_normal(4)
+    for (a, ia), (b, ib) in [(("f1", "f1"), ("f2", "f2")), (("f2", "f3"), ("f1", "f1")), (("f1", "f3"), ("f3", "f3"))]:
+        ls = Lowered(fs, sb.GPPPInput(a, sb.GPPPInput(ia, x0)))
+        lt = Lowered(fs, sb.GPPPInput(b, sb.GPPPInput(ib, x1)))
+        K = eval_dense(spec_dense(ls, lt))
+        Ko = orc.cov(fo, orc.GPPPInput(a, orc.GPPPInput(ia, x0)), orc.GPPPInput(b, orc.GPPPInput(ib, x1)))
+        assert np.allclose(K, Ko, rtol=1e-13, atol=1e-14)
+        assert np.allclose(ls.mean(), orc.mean(fo, orc.GPPPInput(a, orc.GPPPInput(ia, x0))), rtol=1e-14)
+        assert np.allclose(eval_diag(spec_diag(ls)), orc.var(fo, orc.GPPPInput(a, orc.GPPPInput(ia, x0))), rtol=1e-13)
+    # different outer wrappers of the same inner programme are independent => no terms at all
+    assert spec_dense(Lowered(fs, sb.GPPPInput("f1", sb.GPPPInput("f1", x0))),
+                      Lowered(fs, sb.GPPPInput("f3", sb.GPPPInput("f1", x1)))).nterms == 0
