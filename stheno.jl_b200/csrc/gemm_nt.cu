@@ -196,6 +196,10 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
 
     if (warp == MATH_WARPS) {
         // ================= TMA producer warp =================
+        // (SB_ABLATE_* are compile-time ablations used by tools/bench_gemm only -- wrong results,
+        //  timing experiments: NO_TMA = no bulk copies at all, NO_WAIT = copies issued but the
+        //  math warps never wait for them.  See DESIGN.md K3 and profiles/.)
+#ifndef SB_ABLATE_NO_TMA
         if (lane == 0) {
             TileCursor pcur;
             pcur.init(g, blockIdx.x);
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
                 }
             }
         }
+#endif
         return;
     }
 
@@ -261,7 +266,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
         const TilePtrs tp = cur.ptrs(g);
         const double* b_base = b_base0;
         for (int c = 0; c < nchunks; c++) {
+#if !defined(SB_ABLATE_NO_TMA) && !defined(SB_ABLATE_NO_WAIT)
             mbar_wait(&full[slot], phase);
+#endif
             const double* a = a_base + slot * SLAB;
             const double* b = b_base + slot * SLAB_B;
 #pragma unroll
@@ -277,7 +284,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
                     for (int i = 0; i < 4; i++) dmma(acc[j][i], cf[j], rf[i]);
             }
             __syncwarp();
+#ifndef SB_ABLATE_NO_TMA
             if (lane == 0) mbar_arrive(&empty[slot]);
+#endif
             if (++slot == STAGES) { slot = 0; phase ^= 1; }
         }
 
