@@ -196,9 +196,10 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
 
     if (warp == MATH_WARPS) {
         // ================= TMA producer warp =================
-        // (SB_ABLATE_* are compile-time ablations used by tools/bench_gemm only -- wrong results,
-        //  timing experiments: NO_TMA = no bulk copies at all, NO_WAIT = copies issued but the
-        //  math warps never wait for them.  See DESIGN.md K3 and profiles/.)
+        // (SB_ABLATE_NO_TMA is a compile-time ablation used by tools/bench_gemm only -- wrong
+        //  results, timing experiment: no bulk copies at all.  See DESIGN.md K3 and profiles/.
+        //  The earlier "NO_WAIT" ablation (copies issued, nobody waits) belongs to the pre-
+        //  warp-specialised kernel; here it would alias the empty[] parity and deadlock.)
 #ifndef SB_ABLATE_NO_TMA
         if (lane == 0) {
             TileCursor pcur;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(const __grid_consta
         const TilePtrs tp = cur.ptrs(g);
         const double* b_base = b_base0;
         for (int c = 0; c < nchunks; c++) {
-#if !defined(SB_ABLATE_NO_TMA) && !defined(SB_ABLATE_NO_WAIT)
+#ifndef SB_ABLATE_NO_TMA
             mbar_wait(&full[slot], phase);
 #endif
             const double* a = a_base + slot * SLAB;
