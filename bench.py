@@ -308,9 +308,9 @@ def gpu_main(args):
                            "tcgen05 has no fp64 kind",
             "launches": tm["trailing_launches"] // max(1, args.steps),
             "flops_per_step": tm["trailing_flops"] / args.steps,
-            # one `ncu --set full` capture of the first K=256 trailing launch of an N=32768
-            # factorisation (profiles/ncu_gemm_nt_r1.txt): dram read 6.97 GB + write 4.35 GB against
-            # 8.32 GB algorithmic (C read + write of 32385 blocks; operand re-reads are the excess)
+            # one `ncu --set full` capture of a K=256 trailing launch of an N=32768 factorisation
+            # (profiles/ncu_gemm_nt_r1.txt): dram read 6.97 GB + write 4.35 GB against 8.32 GB
+            # algorithmic (C read + write of 32385 blocks; operand re-reads missing L2 are the excess)
             "traffic": 11.32e9, "traffic_algorithmic": 8.32e9,
             "traffic_note": "bytes for ONE captured launch (N=32768, step 0), not the per-step average"}
     hbm_peak = 6575.8
