@@ -203,7 +203,7 @@ _default_ctx = None
 def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:
-        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("SB_USE_LOCAL_RANK") else 0)
+        _default_ctx = Context(int(os.environ.get("SB_DEVICE", "0")))
     return _default_ctx
 
 
