@@ -33,6 +33,19 @@ SIGMA2 = 0.1
 DMMA_PEAK_TFLOPS = 37.1  # builder-measured, tools/mb_fp64_peak.cu on this pool's B200 (profiles/)
 
 
+_OUT_FD = None  # set by main(): the process's ORIGINAL stdout; fd 1 itself is pointed at stderr
+
+
+def emit(line: str):
+    """Print the one JSON line.  Under main() everything else that writes to fd 1 (NCCL's version
+    banner, torch warnings from C++) has been diverted to stderr, so stdout carries only this."""
+    if _OUT_FD is None:
+        print(line)
+        sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, (line + "\n").encode())
+
+
 def make_inputs(n, ns):
     """x ~ U(0, n/32) (32 points per length-scale), y = sin(x)+0.3 eps."""
     rng = np.random.default_rng(123456)
@@ -294,7 +307,17 @@ def gpu_main(args):
     h2d = 8 * (n + n + n + ns + n)  # x (factor), delta (logpdf), delta (posterior), x*, x (cross spec)
     d2h = 8 * (2 * ns + 1)
 
+    def shutdown():
+        # collective, orderly teardown: NCCL communicator of the library first, then torch's
+        if dist is not None:
+            dist.barrier()
+        sblib.set_default_context(None)
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+
     if rank != 0:
+        shutdown()
         return
     np.testing.assert_allclose(mean_d.cpu().numpy(), m_e, rtol=1e-9, atol=1e-10)
 
@@ -350,7 +373,8 @@ def gpu_main(args):
     }
     if cb:
         out["cpu_baseline"] = cb
-    print(json.dumps(out))
+    emit(json.dumps(out))
+    shutdown()
 
 
 def reference_main(args):
@@ -381,7 +405,7 @@ def reference_main(args):
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 def main():
@@ -394,6 +418,10 @@ def main():
     ap.add_argument("--ns", type=int, default=N_TEST)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)  # from here on fd 1 == stderr for Python AND C libraries
     if args.impl == "reference":
         reference_main(args)
     else:
