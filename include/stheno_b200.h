@@ -193,6 +193,11 @@ int32_t sb_factor_logdet(sb_ctx* ctx, sb_factor* f, double* out);
 int32_t sb_logpdf(sb_ctx* ctx, sb_factor* f, const void* delta, int32_t S, double* out);
 int32_t sb_factor_set_data(sb_ctx* ctx, sb_factor* f, const void* delta);
 int32_t sb_factor_alpha(sb_ctx* ctx, sb_factor* f, void* alpha_out);
+/* sb_factor_set_alpha: install a previously computed alpha (N values) as the handle's current
+ * posterior weights.  `posterior(fx, y)` is a pure function in the reference (AbstractGPs
+ * PosteriorGP keeps its own alpha next to the shared Cholesky): two posteriors built from one fx
+ * share the device factor and each re-installs its alpha before predicting. */
+int32_t sb_factor_set_alpha(sb_ctx* ctx, sb_factor* f, const void* alpha);
 int32_t sb_predict(sb_ctx* ctx, sb_factor* f, const sb_covspec* cross,
                    const sb_covspec* prior_diag, void* mean_out, void* var_out);
 int32_t sb_predict_cov(sb_ctx* ctx, sb_factor* f, const sb_covspec* cross,
@@ -219,6 +224,11 @@ int32_t sb_vfe_create(sb_ctx* ctx, const sb_covspec* uu, const sb_noise* noise_u
                       const void* delta, sb_vfe** out, double* out2, int64_t* info);
 int32_t sb_vfe_predict(sb_ctx* ctx, sb_vfe* v, const sb_covspec* cross /* N* x M */,
                        const sb_covspec* prior_diag, void* mean_out, void* var_out);
+/* sb_vfe_predict_cov replaces  cov(f_approx_post(x*)) = K** - B'B + (L_Lambda^{-1}B)'(L_Lambda^{-1}B)
+ * with B = L_u^{-1} K_u*  (AbstractGPs approximate posterior);
+ * prior_full = cov(prior, x*) dense spec, cov_out column-major N* x N*. */
+int32_t sb_vfe_predict_cov(sb_ctx* ctx, sb_vfe* v, const sb_covspec* cross /* N* x M */,
+                           const sb_covspec* prior_full, void* cov_out);
 int32_t sb_vfe_destroy(sb_vfe* v);
 
 #ifdef __cplusplus

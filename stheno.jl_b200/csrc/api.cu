@@ -142,13 +142,14 @@ struct sb_factor {
     int64_t N = 0, Np = 0;
     Packed L{nullptr, 0};
     double* invL = nullptr;
+    double* ldiag = nullptr;  // multi-GPU only: contiguous copies of the diagonal blocks L_kk (broadcast payload)
     double* logdet_blk = nullptr;
     long long* info_dev = nullptr;
     double* panel = nullptr;  // 2 x (Np x NB) panel buffers
     double* alpha = nullptr;  // Np
     bool has_alpha = false;
     double logdet = 0.0;
-    size_t bytes_L = 0, bytes_invL = 0, bytes_ld = 0, bytes_panel = 0, bytes_alpha = 0;
+    size_t bytes_L = 0, bytes_invL = 0, bytes_ld = 0, bytes_panel = 0, bytes_alpha = 0, bytes_ldiag = 0;
 };
 
 namespace {
@@ -326,14 +327,21 @@ int32_t assemble_diag(sb_ctx* c, DevSpec& ds, double* out) {
 // rank holds the complete factor and the solves need no communication.
 struct CholEv { cudaEvent_t e[4]; };
 
-static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, size_t slab_elems, int owner) {
-    cudaStream_t st = c->stream;
+// One grouped broadcast per panel: inverse of the diagonal block, the diagonal block itself, its
+// logdet share and the tiled sub-diagonal panel.  Non-owners drop L_kk into their packed matrix, so
+// after the sweep every rank holds the complete factor without any extra collective.
+static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, size_t slab_elems, int owner,
+                           cudaStream_t st) {
+    const int64_t bo = k * (int64_t)NB * NB;
     SB_NCCL(nccl_dl::GroupStart());
-    SB_NCCL(nccl_dl::Broadcast(f->invL + k * (int64_t)NB * NB, f->invL + k * (int64_t)NB * NB,
-                               (size_t)NB * NB, ncclDouble, owner, c->comm, st));
+    SB_NCCL(nccl_dl::Broadcast(f->invL + bo, f->invL + bo, (size_t)NB * NB, ncclDouble, owner, c->comm, st));
+    SB_NCCL(nccl_dl::Broadcast(f->ldiag + bo, f->ldiag + bo, (size_t)NB * NB, ncclDouble, owner, c->comm, st));
     SB_NCCL(nccl_dl::Broadcast(f->logdet_blk + k, f->logdet_blk + k, 1, ncclDouble, owner, c->comm, st));
     if (slab_elems) SB_NCCL(nccl_dl::Broadcast(Pslab, Pslab, slab_elems, ncclDouble, owner, c->comm, st));
     SB_NCCL(nccl_dl::GroupEnd());
+    if (owner != c->rank)
+        SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k, k), f->L.ld(k) * sizeof(double), f->ldiag + bo, NB * sizeof(double),
+                                  NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
     return SB_OK;
 }
 
@@ -345,8 +353,10 @@ static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, si
 // serial potrf/TRSM/broadcast chain leaves the critical path.  Two sets of tiled panel buffers.
 constexpr int LOOKAHEAD_SMS = 8;
 
+struct CommEv { cudaEvent_t a, b; };
+
 static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* const* Pw, const double* const* Pt,
-                           int rank, int world, cudaStream_t st) {
+                           int rank, int world, cudaStream_t st, std::vector<CommEv>* comm_ev) {
     const int64_t Np = f->Np;
     for (int q = 0; q < nq; q++) {
         const int64_t kq = k0 + q;
@@ -355,27 +365,27 @@ static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* 
         double* Pq = Pw[q] + tiled_panel_elems((int64_t)q * NB);
         if (owner == rank) {
             if (q > 0) launch_syrk_packed(f->L, k0, Pt, q, kq, kq + 1, rank, world, st);
-            launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st);
+            launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st, world > 1 ? f->ldiag : nullptr);
             if (mq > 0)
                 launch_trsm_tiled(f->L.blk(kq + 1, kq), f->L.ld(kq), f->invL + kq * (int64_t)NB * NB, Pq, mq, st);
         }
         if (world > 1) {
-            SB_NCCL(nccl_dl::GroupStart());
-            SB_NCCL(nccl_dl::Broadcast(f->invL + kq * (int64_t)NB * NB, f->invL + kq * (int64_t)NB * NB,
-                                       (size_t)NB * NB, ncclDouble, owner, c->comm, st));
-            SB_NCCL(nccl_dl::Broadcast(f->logdet_blk + kq, f->logdet_blk + kq, 1, ncclDouble, owner, c->comm, st));
-            if (mq > 0)
-                SB_NCCL(nccl_dl::Broadcast(Pq, Pq, (size_t)tiled_panel_elems(mq), ncclDouble, owner, c->comm, st));
-            SB_NCCL(nccl_dl::GroupEnd());
+            CommEv ce{nullptr, nullptr};
+            if (comm_ev && c->fine_timing) {
+                ce.a = c->next_event(); ce.b = c->next_event();
+                SB_CUDA(cudaEventRecord(ce.a, st));
+            }
+            SB_TRY(bcast_panel(c, f, kq, Pq, mq > 0 ? (size_t)tiled_panel_elems(mq) : 0, owner, st));
+            if (ce.a) { SB_CUDA(cudaEventRecord(ce.b, st)); comm_ev->push_back(ce); }
         }
         if (mq > 0) launch_untile_panel(Pt[q], q, mq / NB, f->L.blk(kq + 1, kq), f->L.ld(kq), st);
     }
     return SB_OK;
 }
 
-static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f) {
+static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) {
     const int64_t nblk = f->L.nblk(), Np = f->Np;
-    const int world = c->world, rank = c->rank;
+    std::vector<CommEv> comm_ev;
     cudaStream_t s1 = c->stream, s2 = c->stream2;
     const int64_t nsteps = (nblk + OUTER_BLOCKS - 1) / OUTER_BLOCKS;
     double* Pw[2][OUTER_BLOCKS];
@@ -393,7 +403,7 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f) {
     SB_CUDA(cudaStreamWaitEvent(s2, e_start, 0));
     {
         const int nq0 = (int)(nblk < OUTER_BLOCKS ? nblk : OUTER_BLOCKS);
-        SB_TRY(panel_phase(c, f, 0, nq0, Pw[0], Pt[0], rank, world, s2));
+        SB_TRY(panel_phase(c, f, 0, nq0, Pw[0], Pt[0], rank, world, s2, &comm_ev));
         SB_CUDA(cudaEventRecord(ev_p[0], s2));
     }
     double flops = 0;
@@ -412,7 +422,7 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f) {
             if (s + 1 < nsteps) {
                 const int nq1 = (int)(nblk - jt < OUTER_BLOCKS ? nblk - jt : OUTER_BLOCKS);
                 SB_CUDA(cudaStreamWaitEvent(s2, ev_a[s], 0));
-                SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2));
+                SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2, &comm_ev));
                 SB_CUDA(cudaEventRecord(ev_p[s + 1], s2));
             }
             if (jA < nblk) launch_syrk_packed(f->L, k0, Pt[set], nq, jA, nblk, rank, world, s1, LOOKAHEAD_SMS);  // T^B
@@ -435,20 +445,34 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f) {
         float ms = 0;
         cudaEventElapsedTime(&ms, e_start, ev_p[0]);
         c->tm.panel_ms += ms;  // only the first, un-hidden panel phase is on the critical path
+        // NCCL time on the look-ahead stream (overlapped with T^B except for the first phase):
+        // the interval includes waiting for the owner's potrf/TRSM on the other ranks
+        for (auto& ce : comm_ev) {
+            float cm = 0;
+            cudaEventElapsedTime(&cm, ce.a, ce.b);
+            c->tm.comm_ms += cm;
+        }
     }
     c->tm.trailing_flops += flops;
     c->tm.trailing_launches += nlaunch;
     return SB_OK;
 }
 
-static int32_t sync_diag_blocks_and_info(sb_ctx* c, sb_factor* f);
+static int32_t sync_info(sb_ctx* c, sb_factor* f);
 
 int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     const int64_t nblk = f->L.nblk();
     const int world = force_local ? 1 : c->world, rank = force_local ? 0 : c->rank;
-    if (world > 1 && !getenv("SB_NO_LOOKAHEAD")) {
-        SB_TRY(cholesky_lookahead(c, f));
-        return sync_diag_blocks_and_info(c, f);
+    // look-ahead (panel phase of step s+1 on stream 2 under the big trailing update of step s) also
+    // pays on ONE GPU: the serial potrf/TRSM chain (106 ms at N=65536) leaves the critical path
+    static const bool no_la = getenv("SB_NO_LOOKAHEAD") != nullptr;
+    if (!no_la && nblk > OUTER_BLOCKS) {
+        SB_TRY(cholesky_lookahead(c, f, world, rank));
+        if (world > 1) {
+            SB_TRY(sync_info(c, f));
+            SB_CUDA(cudaStreamSynchronize(c->stream));  // callers read info / logdet with blocking copies
+        }
+        return SB_OK;
     }
     const int64_t Np = f->Np;
     cudaStream_t st = c->stream;
@@ -481,12 +505,12 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
             if (owner == rank) {
                 // bring block column kq up to date with the panels already factored in this outer step
                 if (q > 0) launch_syrk_packed(f->L, k0, Pt, q, kq, kq + 1, rank, world, st);
-                launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st);
+                launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st, world > 1 ? f->ldiag : nullptr);
                 if (mq > 0)
                     launch_trsm_tiled(f->L.blk(kq + 1, kq), f->L.ld(kq), f->invL + kq * (int64_t)NB * NB, Pq, mq, st);
             }
             markk(0);
-            if (world > 1) SB_TRY(bcast_panel(c, f, kq, Pq, mq > 0 ? (size_t)tiled_panel_elems(mq) : 0, owner));
+            if (world > 1) SB_TRY(bcast_panel(c, f, kq, Pq, mq > 0 ? (size_t)tiled_panel_elems(mq) : 0, owner, st));
             markk(1);
             if (mq > 0) launch_untile_panel(Pt[q], q, mq / NB, f->L.blk(kq + 1, kq), f->L.ld(kq), st);
         }
@@ -502,7 +526,7 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
             }
         }
     }
-    if (world > 1) SB_TRY(sync_diag_blocks_and_info(c, f));
+    if (world > 1) SB_TRY(sync_info(c, f));
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaStreamSynchronize(st));
     if (ft) {
@@ -520,35 +544,21 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     return SB_OK;
 }
 
-static int32_t sync_diag_blocks_and_info(sb_ctx* c, sb_factor* f) {
-    const int64_t nblk = f->L.nblk();
-    const int world = c->world, rank = c->rank;
+// info = first failing pivot over all ranks (0 = ok): min over ranks of (info ? info : INT64_MAX),
+// mapped on the device -- one tiny all-reduce, no host round trip.
+__global__ void info_map_kernel(long long* info, int back) {
+    const long long big = 0x7fffffffffffffffLL;
+    if (back) { if (*info == big) *info = 0; }
+    else      { if (*info == 0) *info = big; }
+}
+
+static int32_t sync_info(sb_ctx* c, sb_factor* f) {
     cudaStream_t st = c->stream;
-        // the diagonal blocks themselves live only on their owners so far: share them so every
-        // rank holds the complete factor (needed by the replicated / RHS-sharded solves)
-        for (int64_t k = 0; k < nblk; k++) {
-            int owner = (int)(k % world);
-            double* tmp = f->panel;  // pack L_kk (NB columns strided by ld(k)) through the panel buffer
-            if (owner == rank)
-                SB_CUDA(cudaMemcpy2DAsync(tmp, NB * sizeof(double), f->L.blk(k, k), f->L.ld(k) * sizeof(double),
-                                          NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
-            SB_NCCL(nccl_dl::Broadcast(tmp, tmp, (size_t)NB * NB, ncclDouble, owner, c->comm, st));
-            if (owner != rank)
-                SB_CUDA(cudaMemcpy2DAsync(f->L.blk(k, k), f->L.ld(k) * sizeof(double), tmp, NB * sizeof(double),
-                                          NB * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
-        }
-        // first failing pivot over all ranks: min over ranks of (info ? info : INT64_MAX)
-        long long h = 0;
-        SB_CUDA(cudaMemcpyAsync(&h, f->info_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        if (h == 0) h = 0x7fffffffffffffffLL;
-        SB_CUDA(cudaMemcpyAsync(f->info_dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-        SB_NCCL(nccl_dl::AllReduce(f->info_dev, f->info_dev, 1, ncclInt64, ncclMin, c->comm, st));
-        SB_CUDA(cudaMemcpyAsync(&h, f->info_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        if (h == 0x7fffffffffffffffLL) h = 0;
-        SB_CUDA(cudaMemcpyAsync(f->info_dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaStreamSynchronize(st));
+    info_map_kernel<<<1, 1, 0, st>>>(f->info_dev, 0);
+    SB_NCCL(nccl_dl::AllReduce(f->info_dev, f->info_dev, 1, ncclInt64, ncclMin, c->comm, st));
+    info_map_kernel<<<1, 1, 0, st>>>(f->info_dev, 1);
+    g_launch_count += 2;
+    SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
 
@@ -737,6 +747,7 @@ int32_t sb_factor_destroy(sb_factor* f) {
     sb_ctx* c = f->ctx;
     c->pool_release(f->L.base, f->bytes_L);
     c->pool_release(f->invL, f->bytes_invL);
+    c->pool_release(f->ldiag, f->bytes_ldiag);
     c->pool_release(f->logdet_blk, f->bytes_ld);
     c->pool_release(f->info_dev, 8);
     c->pool_release(f->panel, f->bytes_panel);
@@ -766,9 +777,11 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
     f->bytes_ld = (size_t)nblk * sizeof(double);
     f->bytes_panel = (size_t)2 * OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);
     f->bytes_alpha = (size_t)f->Np * sizeof(double);
+    f->bytes_ldiag = c->world > 1 ? f->bytes_invL : 0;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->L.base, f->bytes_L);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->invL, f->bytes_invL);
+    if (e == cudaSuccess && f->bytes_ldiag) e = c->pool_alloc((void**)&f->ldiag, f->bytes_ldiag);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->logdet_blk, f->bytes_ld);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->info_dev, 8);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->panel, f->bytes_panel);
@@ -817,12 +830,8 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
 
     DevSpec ds(c);
     SB_TRY(ds.build(spec, c->stream, false));
-    sb_factor* f = new sb_factor();
-    f->ctx = c;
-    f->N = spec->nrows;
-    f->Np = round_up(f->N, NB);
-    f->L.Np = f->Np;
-    const int64_t nblk = f->L.nblk();
+    sb_factor* f = nullptr;
+    SB_TRY(factor_alloc(c, spec->nrows, &f));
     auto fail = [&](int32_t s) {
         sb_factor_destroy(f);
         return s;
@@ -832,25 +841,11 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
         cudaError_t _e = (call);                                               \
         if (_e != cudaSuccess) return fail(sb::cuda_fail(_e, #call, __FILE__, __LINE__)); \
     } while (0)
-    f->bytes_L = (size_t)f->L.total() * sizeof(double);
-    f->bytes_invL = (size_t)nblk * NB * NB * sizeof(double);
-    f->bytes_ld = (size_t)nblk * sizeof(double);
-    f->bytes_panel = (size_t)2 * OUTER_BLOCKS * tiled_panel_elems(f->Np) * sizeof(double);  // 2 sets (look-ahead) of tiled panels
-    f->bytes_alpha = (size_t)f->Np * sizeof(double);
-    SB_CUDA_F(c->pool_alloc((void**)&f->L.base, f->bytes_L));
-    SB_CUDA_F(c->pool_alloc((void**)&f->invL, f->bytes_invL));
-    SB_CUDA_F(c->pool_alloc((void**)&f->logdet_blk, f->bytes_ld));
-    SB_CUDA_F(c->pool_alloc((void**)&f->info_dev, 8));
-    SB_CUDA_F(c->pool_alloc((void**)&f->panel, f->bytes_panel));
-    SB_CUDA_F(c->pool_alloc((void**)&f->alpha, f->bytes_alpha));
-    SB_CUDA_F(cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream));
-    SB_CUDA_F(cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream));
-
+    const int a_rank = force_local ? 0 : c->rank, a_world = force_local ? 1 : c->world;
     DevBuf nd(c), ndense(c);
     const double* noise_diag = nullptr;
     double sigma2 = 0.0;
     if (noise && noise->dense) {
-        SB_CHECK(f->N <= 65535, "dense observation noise: N <= 65535");
         if (ndense.alloc((size_t)f->N * f->N * sizeof(double)) != SB_OK) return fail(SB_ERR_NOMEM);
         SB_CUDA_F(cudaMemcpyAsync(ndense.p, noise->dense, (size_t)f->N * f->N * sizeof(double), cudaMemcpyDefault, c->stream));
     } else if (noise) {
@@ -863,42 +858,23 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
     }
     {
         PhaseTimer t(c, &c->tm.assemble_ms);
-        for (auto& b : ds.blocks) {
-            // multi-GPU: every rank assembles only the block columns it owns (plus nothing else);
-            // the kernel skips foreign tiles via the ownership test below (single GPU: all).
-            launch_assemble_packed(b, f->L, f->N, sigma2, noise_diag, c->stream);
-        }
+        // multi-GPU: every rank assembles only the block columns it owns under the Cholesky
+        // distribution (the kernel skips foreign tiles); foreign columns arrive as broadcast panels
+        for (auto& b : ds.blocks) launch_assemble_packed(b, f->L, f->N, sigma2, noise_diag, c->stream, a_rank, a_world);
         if (ndense.p) launch_add_dense_lower(f->L, ndense.d(), f->N, f->N, c->stream);
         launch_fill_padding(f->L, f->N, c->stream);
         t.stop();
         SB_CUDA_F(cudaGetLastError());
-        int32_t s = cholesky_packed(c, f, force_local);
+        int32_t s = factor_finish(c, f, info, force_local);
         if (s != SB_OK) return fail(s);
         t.collect();
     }
-    long long h_info = 0;
-    std::vector<double> ld(nblk);
-    SB_CUDA_F(cudaMemcpy(&h_info, f->info_dev, sizeof(long long), cudaMemcpyDeviceToHost));
-    SB_CUDA_F(cudaMemcpy(ld.data(), f->logdet_blk, nblk * sizeof(double), cudaMemcpyDeviceToHost));
     cudaEventRecord(t1, c->stream);
     cudaEventSynchronize(t1);
     float ms = 0;
     cudaEventElapsedTime(&ms, t0, t1);
     c->tm.total_ms += ms;
     count_launches(c, before);
-    if (c->world > 1) {
-        // info lives on the owner of the failing block; take the max over ranks (0 = ok)
-        // (cheap host-side path: every rank already has all logdet_blk via broadcast)
-    }
-    if (h_info != 0) {
-        if (info) *info = (int64_t)h_info;
-        sb::set_error("matrix is not positive definite; Cholesky factorization failed at pivot " +
-                      std::to_string(h_info));
-        return fail(SB_ERR_NOT_POSDEF);
-    }
-    double s = 0.0;
-    for (double v : ld) s += v;
-    f->logdet = s;
     *out = f;
     return SB_OK;
 #undef SB_CUDA_F
@@ -947,6 +923,18 @@ int32_t sb_factor_set_data(sb_ctx* c, sb_factor* f, const void* delta) {
     t.collect();
     f->has_alpha = true;
     count_launches(c, before);
+    return SB_OK;
+}
+
+// posterior(fx, y) is a pure function in the reference (AbstractGPs PosteriorGP holds its own
+// alpha): a host object that shares the factor with other posteriors re-installs ITS alpha here
+// before predicting.
+int32_t sb_factor_set_alpha(sb_ctx* c, sb_factor* f, const void* alpha) {
+    SB_CHECK(c && f && alpha, "null argument");
+    begin_call(c);
+    SB_TRY(upload_padded(c, alpha, f->N, f->Np, 1, f->alpha));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    f->has_alpha = true;
     return SB_OK;
 }
 
@@ -1074,10 +1062,16 @@ static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
                 // posterior covariance (+ noise) -> packed layout -> Cholesky, all on device
                 sb_factor* fn = nullptr;
                 SB_TRY(factor_alloc(c, Ns, &fn));
-                DevBuf nd(c);
+                DevBuf nd(c), ndn(c);
                 double s2 = post_noise ? post_noise->sigma2 : 0.0;
-                launch_pack_lower(fn->L, Cm.d(), Nsp, (post_noise && post_noise->diag) ? 0.0 : s2, c->stream);
-                if (post_noise && post_noise->diag) {
+                const bool pn_dense = post_noise && post_noise->dense;
+                launch_pack_lower(fn->L, Cm.d(), Nsp, (pn_dense || (post_noise && post_noise->diag)) ? 0.0 : s2, c->stream);
+                if (pn_dense) {  // f_post(x*, Sigma_dense): add the lower triangle of the full noise matrix
+                    int32_t st2 = ndn.alloc((size_t)Ns * Ns * sizeof(double));
+                    if (st2 != SB_OK) { sb_factor_destroy(fn); return st2; }
+                    cudaMemcpyAsync(ndn.p, post_noise->dense, (size_t)Ns * Ns * sizeof(double), cudaMemcpyDefault, c->stream);
+                    launch_add_dense_lower(fn->L, ndn.d(), Ns, Ns, c->stream);
+                } else if (post_noise && post_noise->diag) {
                     int32_t st2 = nd.alloc(Ns * sizeof(double));
                     if (st2 != SB_OK) { sb_factor_destroy(fn); return st2; }
                     cudaMemcpyAsync(nd.p, post_noise->diag, Ns * sizeof(double), cudaMemcpyDefault, c->stream);
@@ -1322,6 +1316,40 @@ int32_t sb_vfe_create(sb_ctx* c, const sb_covspec* uu, const sb_noise* noise_u, 
     return SB_OK;
 #undef VFE_TRY
 #undef VFE_CUDA
+}
+
+// cov(f_approx_post(x*)) = K** - B'B + (L_Lambda^{-1} B)'(L_Lambda^{-1} B),  B = L_u^{-1} K_u*
+// (AbstractGPs approx posterior).  cross: N* x M dense spec, prior_full: N* x N*.
+int32_t sb_vfe_predict_cov(sb_ctx* c, sb_vfe* v, const sb_covspec* cross, const sb_covspec* prior_full,
+                           void* cov_out) {
+    SB_CHECK(c && v && cross && prior_full && cov_out, "null argument");
+    SB_CHECK(cross->ncols == v->M, "cross spec must be N* x M");
+    SB_CHECK(prior_full->nrows == cross->nrows && prior_full->ncols == cross->nrows, "prior spec must be N* x N*");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    const int64_t Ns = cross->nrows, Nsp = round_up(Ns > 0 ? Ns : 1, NB), Mp = v->Mp;
+    if (Ns == 0) return SB_OK;
+    DevSpec dc(c), dp(c);
+    SB_TRY(dc.build(cross, c->stream, false));
+    SB_TRY(dp.build(prior_full, c->stream, false));
+    DevBuf W(c), Xk(c), Cm(c);
+    SB_TRY(W.alloc((size_t)Nsp * Mp * sizeof(double)));
+    SB_TRY(Xk.alloc((size_t)Nsp * 2 * NB * sizeof(double)));
+    SB_TRY(Cm.alloc((size_t)Nsp * Nsp * sizeof(double)));
+    SB_CUDA(cudaMemsetAsync(W.p, 0, (size_t)Nsp * Mp * sizeof(double), c->stream));
+    SB_CUDA(cudaMemsetAsync(Cm.p, 0, (size_t)Nsp * Nsp * sizeof(double), c->stream));
+    SB_TRY(assemble_dense(c, dc, W.d(), Nsp));
+    SB_TRY(assemble_dense(c, dp, Cm.d(), Nsp));
+    SB_TRY(trsm_sweep(c, v->fu, W.d(), Nsp, Xk.d(), true, nullptr));           // W = B'
+    launch_gemm_nt(W.d(), Nsp, W.d(), Nsp, Cm.d(), Nsp, Nsp, Nsp, Mp, -1.0, 1.0, c->stream);
+    SB_TRY(trsm_sweep(c, v->fl, W.d(), Nsp, Xk.d(), true, nullptr));           // W = (L_Lambda^{-1} B)'
+    launch_gemm_nt(W.d(), Nsp, W.d(), Nsp, Cm.d(), Nsp, Nsp, Nsp, Mp, 1.0, 1.0, c->stream);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaMemcpy2DAsync(cov_out, Ns * sizeof(double), Cm.p, Nsp * sizeof(double), Ns * sizeof(double), Ns,
+                              cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    count_launches(c, before);
+    return SB_OK;
 }
 
 int32_t sb_vfe_predict(sb_ctx* c, sb_vfe* v, const sb_covspec* cross, const sb_covspec* prior_diag,

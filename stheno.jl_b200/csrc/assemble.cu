@@ -139,12 +139,15 @@ __device__ __forceinline__ void strip_1d(const TermDev& t, double xa, double xb,
 template <bool PACKED, bool ALL1D>
 __global__ void __launch_bounds__(256)
 assemble_kernel(const __grid_constant__ BlockDev b, OutDense dense, Packed packed, int64_t N, double sigma2,
-                const double* __restrict__ noise_diag) {
+                const double* __restrict__ noise_diag, int rank, int world) {
     const int64_t r_tile0 = (b.row0 / TR) * TR + (int64_t)blockIdx.x * TR;
     const int64_t c_tile0 = (b.col0 / TC) * TC + (int64_t)blockIdx.y * TC;
     if (PACKED) {
         // tile lies in NB-block (I, J); nothing above the block diagonal is stored
         if (r_tile0 / NB < c_tile0 / NB) return;
+        // multi-GPU: a rank generates exactly the block columns it owns under the Cholesky
+        // distribution (1-D block-cyclic); foreign columns arrive later as broadcast panels
+        if (world > 1 && (int)((c_tile0 / NB) % world) != rank) return;
     }
     const int tr = threadIdx.x & 63, tc = threadIdx.x >> 6;
     const int64_t r0 = r_tile0 + 2 * tr;
@@ -261,19 +264,19 @@ dim3 tile_grid(const BlockDev& b) {
 void launch_assemble_dense(const BlockDev& b, OutDense out, cudaStream_t s) {
     if (b.nrows == 0 || b.ncols == 0) return;
     if (all_1d(b))
-        assemble_kernel<false, true><<<tile_grid(b), 256, 0, s>>>(b, out, Packed{nullptr, 0}, 0, 0.0, nullptr);
+        assemble_kernel<false, true><<<tile_grid(b), 256, 0, s>>>(b, out, Packed{nullptr, 0}, 0, 0.0, nullptr, 0, 1);
     else
-        assemble_kernel<false, false><<<tile_grid(b), 256, 0, s>>>(b, out, Packed{nullptr, 0}, 0, 0.0, nullptr);
+        assemble_kernel<false, false><<<tile_grid(b), 256, 0, s>>>(b, out, Packed{nullptr, 0}, 0, 0.0, nullptr, 0, 1);
     g_launch_count++;
 }
 
 void launch_assemble_packed(const BlockDev& b, Packed out, int64_t N, double sigma2,
-                            const double* noise_diag, cudaStream_t s) {
+                            const double* noise_diag, cudaStream_t s, int rank, int world) {
     if (b.nrows == 0 || b.ncols == 0) return;
     if (all_1d(b))
-        assemble_kernel<true, true><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag);
+        assemble_kernel<true, true><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag, rank, world);
     else
-        assemble_kernel<true, false><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag);
+        assemble_kernel<true, false><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag, rank, world);
     g_launch_count++;
 }
 

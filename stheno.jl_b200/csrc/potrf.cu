@@ -19,7 +19,8 @@ constexpr size_t POTRF_SMEM = (size_t)NB * LDS * 8 + (size_t)NPB * PB * PB * 8 +
 
 __global__ void __launch_bounds__(PT, 1)
 potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
-                 double* __restrict__ logdet_blk, long long* __restrict__ info) {
+                 double* __restrict__ logdet_blk, long long* __restrict__ info,
+                 double* __restrict__ ldiag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s = reinterpret_cast<double*>(smem_raw);   // s[c*LDS + r]: the block, column-major
     double* dinv = s + NB * LDS;                       // [NPB][PB*PB]: inverses of the 8x8 diagonal blocks (col-major)
@@ -110,6 +111,11 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
     for (int idx = tid; idx < NB * NB; idx += PT) {
         int r = idx % NB, c = idx / NB;
         Akk[(int64_t)c * ld + r] = s[c * LDS + r];
+    }
+    // multi-GPU: a contiguous copy of L_kk rides along with the panel broadcast
+    if (ldiag != nullptr) {
+        double* ld_out = ldiag + k * (int64_t)NB * NB;
+        for (int idx = tid; idx < NB * NB; idx += PT) ld_out[idx] = s[(idx / NB) * LDS + (idx % NB)];
     }
     if (tid < 32) {
         double acc = 0.0;
@@ -205,13 +211,13 @@ bool g_attr = false;
 }  // namespace
 
 void launch_potrf_inv(Packed A, int64_t k, int64_t N, double* invL, double* logdet_blk,
-                      long long* info, cudaStream_t st) {
+                      long long* info, cudaStream_t st, double* ldiag) {
     if (!g_attr) {
         cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)POTRF_SMEM);
         g_attr = true;
     }
-    potrf_inv_kernel<<<1, PT, POTRF_SMEM, st>>>(A, k, N, invL, logdet_blk, info);
+    potrf_inv_kernel<<<1, PT, POTRF_SMEM, st>>>(A, k, N, invL, logdet_blk, info, ldiag);
     g_launch_count++;
 }
 

@@ -92,15 +92,18 @@ struct OutDense {
 
 // ---- kernel launchers (defined in the .cu files) ------------------------------------------
 void launch_assemble_dense(const BlockDev& b, OutDense out, cudaStream_t s);
+// world > 1: only tiles in block columns J with J % world == rank are generated
 void launch_assemble_packed(const BlockDev& b, Packed out, int64_t N, double sigma2,
-                            const double* noise_diag, cudaStream_t s);
+                            const double* noise_diag, cudaStream_t s, int rank = 0, int world = 1);
 void launch_fill_padding(Packed out, int64_t N, cudaStream_t s);
 void launch_assemble_diag(const BlockDev& b, double* out, cudaStream_t s);
 
 // potrf of diagonal block k (in place in the packed matrix) + explicit inverse of L_kk
 // (dense NB x NB, ld NB) + per-block sum of log pivots + first failing pivot (1-based, 0 = ok)
+// ldiag != nullptr: also store a contiguous copy of L_kk at ldiag + k*NB*NB (multi-GPU: it is
+// broadcast together with the panel so every rank ends up with the complete factor)
 void launch_potrf_inv(Packed A, int64_t k, int64_t N, double* invL, double* logdet_blk,
-                      long long* info, cudaStream_t s);
+                      long long* info, cudaStream_t s, double* ldiag = nullptr);
 
 // C = beta*C + alpha * A * B^T  (all column-major), M x Ncols x K, multiples of 128 / 64 / 16
 void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
@@ -156,6 +159,19 @@ void launch_transpose(const double* in, int64_t ld_in, int64_t rows, int64_t col
 void launch_pack_lower(Packed L, const double* D, int64_t ld, double shift, cudaStream_t st);
 void launch_add_diag(Packed L, const double* d, int64_t n, cudaStream_t st);
 void launch_add_dense_lower(Packed L, const double* D, int64_t ld, int64_t n, cudaStream_t st);
+
+// ---- K3': trailing update on tcgen05 (int8 Ozaki slicing), ozaki.cu ------------------------------
+struct alignas(64) OzMaps { unsigned char a[128]; unsigned char b[128]; };  // two CUtensorMap blobs
+struct OzDesc { uint32_t a_kk_adv, b_kk_adv, a_lbo, b_lbo, sbo, layout; };
+size_t oz_planes_bytes(int64_t Np);                       // 7 digit planes, 512-byte row pitch
+int oz_make_maps(signed char* planes, int64_t Np, int tma_mode, OzMaps* out);
+void oz_default_desc(OzDesc* d, int tma_mode);
+// Pt_dev: DEVICE array of the nseg tiled-panel base pointers of the outer step at block column k0
+void launch_oz_slice(const double* const* Pt_dev, int nseg, int64_t k0, int64_t Np, double* scale, int* expo,
+                     signed char* planes, cudaStream_t s);
+int launch_syrk_ozaki(Packed A, int64_t k, int nseg, int64_t jlo, int64_t jhi, int rank, int world,
+                      const OzMaps* maps, const double* scale, const OzDesc* desc, int tma_mode, cudaStream_t s,
+                      int reserve_sms = 0, int* dbg = nullptr);
 
 extern thread_local int64_t g_launch_count;
 

@@ -167,8 +167,8 @@ __global__ void sub_kernel(double* out, const double* a, const double* b, int64_
 }
 
 __global__ void unpack_lower_kernel(Packed L, int64_t N, double* __restrict__ out) {
-    int64_t c = blockIdx.y;
-    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int64_t c = blockIdx.x;
+    int64_t r = (int64_t)blockIdx.y * 256 + threadIdx.x;
     if (r >= N || c >= N) return;
     out[c * N + r] = (r >= c) ? *L.at(r, c) : 0.0;
 }
@@ -235,8 +235,8 @@ transpose_kernel(const double* __restrict__ in, int64_t ld_in, double* __restric
 // packed lower <- dense (n x n, ld), plus `shift` added on the diagonal
 __global__ void __launch_bounds__(256)
 pack_lower_kernel(Packed L, const double* __restrict__ D, int64_t ld, double shift) {
-    int64_t c = blockIdx.y;
-    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int64_t c = blockIdx.x;
+    int64_t r = (int64_t)blockIdx.y * 256 + threadIdx.x;
     if (r >= L.Np || r / NB < c / NB) return;
     double v = D[c * ld + r];
     if (r == c) v += shift;
@@ -254,8 +254,8 @@ untile_panel_kernel(const double* __restrict__ Pt, int64_t row_blk0, double* __r
 // packed lower += dense symmetric matrix (n x n, ld), lower triangle only
 __global__ void __launch_bounds__(256)
 add_dense_lower_kernel(Packed L, const double* __restrict__ D, int64_t ld, int64_t n) {
-    int64_t c = blockIdx.y;
-    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int64_t c = blockIdx.x;
+    int64_t r = (int64_t)blockIdx.y * 256 + threadIdx.x;
     if (r >= n || c >= n || r < c) return;
     *L.at(r, c) += D[c * ld + r];
 }
@@ -269,7 +269,7 @@ __global__ void add_diag_kernel(Packed L, const double* __restrict__ d, int64_t 
 
 void launch_add_dense_lower(Packed L, const double* D, int64_t ld, int64_t n, cudaStream_t st) {
     if (n <= 0) return;
-    add_dense_lower_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, st>>>(L, D, ld, n);
+    add_dense_lower_kernel<<<dim3((unsigned)n, (unsigned)((n + 255) / 256)), 256, 0, st>>>(L, D, ld, n);
     g_launch_count++;
 }
 
@@ -307,7 +307,7 @@ void launch_transpose(const double* in, int64_t ld_in, int64_t rows, int64_t col
 }
 
 void launch_pack_lower(Packed L, const double* D, int64_t ld, double shift, cudaStream_t st) {
-    pack_lower_kernel<<<dim3((unsigned)((L.Np + 255) / 256), (unsigned)L.Np), 256, 0, st>>>(L, D, ld, shift);
+    pack_lower_kernel<<<dim3((unsigned)L.Np, (unsigned)((L.Np + 255) / 256)), 256, 0, st>>>(L, D, ld, shift);
     g_launch_count++;
 }
 
@@ -367,7 +367,7 @@ void launch_sub(double* out, const double* a, const double* b, int64_t n, cudaSt
 }
 
 void launch_unpack_lower(Packed L, int64_t N, double* out, cudaStream_t s) {
-    dim3 grid((unsigned)((N + 255) / 256), (unsigned)N);
+    dim3 grid((unsigned)N, (unsigned)((N + 255) / 256));
     unpack_lower_kernel<<<grid, 256, 0, s>>>(L, N, out);
     g_launch_count++;
 }

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import lib as _lib
 from .gp import GPPP, Lowered, SthenoAbstractGP, spec_dense, spec_diag, spec_symmetric
-from .inputs import npoints
+from .inputs import BlockData, ColVecs, npoints
 
 
 def _ctx():
@@ -31,6 +31,7 @@ class _Factor:
 
     def __init__(self, h, ctx, n):
         self.h, self.ctx, self.n = h, ctx, n
+        self.alpha_owner = None  # the PosteriorGP whose alpha currently sits in the device handle
 
     def __del__(self):
         try:
@@ -259,7 +260,9 @@ def rand(fx, z):
 
 
 class PosteriorGP:
-    """`posterior(fx, y)`: keeps the device factor and alpha = C \\ (y - m)."""
+    """`posterior(fx, y)`: shares the device factor of `fx` and keeps ITS OWN alpha = C \\ (y - m)
+    (AbstractGPs PosteriorGP stores (alpha, C, x, delta); `posterior` is a pure function, so two
+    posteriors built from one fx must not see each other's data)."""
 
     def __init__(self, fx: FiniteGP, y):
         y = np.asarray(y, dtype=np.float64)
@@ -268,17 +271,26 @@ class PosteriorGP:
         self.prior, self.x = fx.prior, fx.x
         self.lx = fx.lowered
         self.fac = fx.factor()
+        self.noise = fx.noise
+        self.y = y
         self.delta = np.ascontiguousarray(y - self.lx.mean())
-        _lib.check(_lib.load().sb_factor_set_data(self.fac.ctx.h, self.fac.h, self.delta.ctypes.data))
+        lib = _lib.load()
+        _lib.check(lib.sb_factor_set_data(self.fac.ctx.h, self.fac.h, self.delta.ctypes.data))
+        self._alpha = np.empty(self.lx.n, dtype=np.float64)
+        _lib.check(lib.sb_factor_alpha(self.fac.ctx.h, self.fac.h, self._alpha.ctypes.data))
+        self.fac.alpha_owner = self
 
     def __call__(self, x, noise=1e-18):
         return FiniteGP(self, x, noise)
 
     @property
     def alpha(self):
-        a = np.empty(self.lx.n, dtype=np.float64)
-        _lib.check(_lib.load().sb_factor_alpha(self.fac.ctx.h, self.fac.h, a.ctypes.data))
-        return a
+        return self._alpha.copy()
+
+    def _install_alpha(self):
+        if self.fac.alpha_owner is not self:
+            _lib.check(_lib.load().sb_factor_set_alpha(self.fac.ctx.h, self.fac.h, self._alpha.ctypes.data))
+            self.fac.alpha_owner = self
 
     def _predict(self, x, want_mean, want_var):
         ls = Lowered(self.prior, x)
@@ -286,6 +298,8 @@ class PosteriorGP:
         pd = spec_diag(ls) if want_var else None
         m = np.empty(ls.n) if want_mean else None
         v = np.empty(ls.n) if want_var else None
+        if want_mean:
+            self._install_alpha()
         _lib.check(_lib.load().sb_predict(
             self.fac.ctx.h, self.fac.h, C.byref(cross), C.byref(pd) if pd is not None else None,
             m.ctypes.data if m is not None else None, v.ctypes.data if v is not None else None))
@@ -303,8 +317,13 @@ class PosteriorGP:
         return self._predict(x, True, True)
 
     def cov(self, x, y=None):
+        """cov(f_post, x) and cov(f_post, x, z) = K(x,z) - (C.U'\\K_{X,x})'(C.U'\\K_{X,z})
+        (AbstractGPs).  The cross form evaluates the joint posterior covariance of
+        the stacked inputs [x; z] on the device and returns its off-diagonal block."""
         if y is not None:
-            raise NotImplementedError("cov(f_post, x, x') is not on the B200 path yet")
+            nx = npoints(x)
+            K = self.cov(_stack_inputs(self.prior, x, y))
+            return np.asfortranarray(K[:nx, nx:])
         ls = Lowered(self.prior, x)
         cross = spec_dense(ls, self.lx)
         full = spec_dense(ls, ls)
@@ -314,13 +333,42 @@ class PosteriorGP:
         return K
 
 
+def _stack_inputs(prior, x, z):
+    """[x; z] as one input collection of `prior` (BlockData for a GPPP, concatenation otherwise)."""
+    if isinstance(prior, GPPP):
+        return BlockData([x, z])
+    if isinstance(x, ColVecs) and isinstance(z, ColVecs):
+        return ColVecs(np.concatenate([x.X, z.X], axis=1))
+    return np.concatenate([np.asarray(x, dtype=np.float64), np.asarray(z, dtype=np.float64)])
+
+
+def _stack_noise(n1, s1, n2, s2):
+    """Sigma_y of the stacked observations [x1; x2]: scalar / vector / matrix noises combined."""
+    if np.ndim(s1) <= 1 and np.ndim(s2) <= 1:
+        d1 = np.full(n1, float(s1)) if np.ndim(s1) == 0 else np.asarray(s1, dtype=np.float64)
+        d2 = np.full(n2, float(s2)) if np.ndim(s2) == 0 else np.asarray(s2, dtype=np.float64)
+        return np.concatenate([d1, d2])
+    S = np.zeros((n1 + n2, n1 + n2))
+    S[:n1, :n1] = np.diag(np.full(n1, float(s1))) if np.ndim(s1) == 0 else (np.diag(s1) if np.ndim(s1) == 1 else s1)
+    S[n1:, n1:] = np.diag(np.full(n2, float(s2))) if np.ndim(s2) == 0 else (np.diag(s2) if np.ndim(s2) == 1 else s2)
+    return S
+
+
 def posterior(fx, y):
     if isinstance(fx, SparseFiniteGP):
         return approx_posterior(VFE(fx.finducing), fx.fobs, y)
     if isinstance(fx, VFE):
         raise TypeError("use posterior(VFE(fz), fx, y)")
     if fx.post is not None:
-        raise NotImplementedError("posterior of a posterior is not on the B200 path yet")
+        # posterior(f_post(x2, s2), y2): sequential conditioning == conditioning the prior on the
+        # stacked observations [x1; x2] with block-diagonal noise (AbstractGPs updates the Cholesky
+        # instead; same distribution).  One joint factorisation on the device.
+        p1 = fx.post
+        if not isinstance(p1, PosteriorGP):
+            raise NotImplementedError("posterior of an approximate (VFE) posterior is not on the B200 path")
+        n1, n2 = npoints(p1.x), len(fx)
+        joint = FiniteGP(p1.prior, _stack_inputs(p1.prior, p1.x, fx.x), _stack_noise(n1, p1.noise, n2, fx.noise))
+        return PosteriorGP(joint, np.concatenate([p1.y, np.asarray(y, dtype=np.float64)]))
     return PosteriorGP(fx, y)
 
 
@@ -427,7 +475,18 @@ class ApproxPosteriorGP:
         return self._predict(x, True, True)
 
     def cov(self, x, y=None):
-        raise NotImplementedError("full approximate-posterior covariance is not on the B200 path yet")
+        """K** - B'B + (Lambda.U'\\B)'(Lambda.U'\\B) with B = U' \\ K_{z*} (AbstractGPs approx posterior)."""
+        if y is not None:
+            nx = npoints(x)
+            K = self.cov(_stack_inputs(self.prior, x, y))
+            return np.asfortranarray(K[:nx, nx:])
+        ls = Lowered(self.prior, x)
+        cross = spec_dense(ls, self.lz)
+        full = spec_dense(ls, ls)
+        K = np.empty((ls.n, ls.n), dtype=np.float64, order="F")
+        _lib.check(_lib.load().sb_vfe_predict_cov(self.handle.ctx.h, self.handle.h, C.byref(cross), C.byref(full),
+                                                  K.ctypes.data))
+        return K
 
 
 def approx_posterior(v: VFE, fx: FiniteGP, y):

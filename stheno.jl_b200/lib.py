@@ -55,8 +55,8 @@ EXPORTS = [
     "sb_ctx_destroy", "sb_ctx_timings", "sb_ctx_mark", "sb_ctx_elapsed_ms", "sb_owner_of_block",
     "sb_owned_trailing_tiles", "sb_row_chunk", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
     "sb_factor_destroy", "sb_factor_logdet", "sb_logpdf", "sb_factor_set_data", "sb_factor_alpha",
-    "sb_predict", "sb_predict_cov", "sb_predict_factor", "sb_rand", "sb_factor_get_L", "sb_vfe_create", "sb_vfe_predict",
-    "sb_vfe_destroy",
+    "sb_factor_set_alpha", "sb_predict", "sb_predict_cov", "sb_predict_factor", "sb_rand", "sb_factor_get_L",
+    "sb_vfe_create", "sb_vfe_predict", "sb_vfe_predict_cov", "sb_vfe_destroy",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def load():
         "sb_logpdf": [vp, vp, vp, i32, P(C.c_double)],
         "sb_factor_set_data": [vp, vp, vp],
         "sb_factor_alpha": [vp, vp, vp],
+        "sb_factor_set_alpha": [vp, vp, vp],
         "sb_predict": [vp, vp, P(sb_covspec), P(sb_covspec), vp, vp],
         "sb_predict_cov": [vp, vp, P(sb_covspec), P(sb_covspec), vp],
         "sb_predict_factor": [vp, vp, P(sb_covspec), P(sb_covspec), P(sb_noise), P(vp), P(i64)],
@@ -114,6 +115,7 @@ def load():
         "sb_vfe_create": [vp, P(sb_covspec), P(sb_noise), P(sb_covspec), P(sb_covspec), P(sb_noise), vp,
                           P(vp), P(C.c_double), P(i64)],
         "sb_vfe_predict": [vp, vp, P(sb_covspec), P(sb_covspec), vp, vp],
+        "sb_vfe_predict_cov": [vp, vp, P(sb_covspec), P(sb_covspec), vp],
         "sb_vfe_destroy": [vp],
     }
     for name, args in sigs.items():

@@ -230,7 +230,9 @@ def test_vfe_pseudo_points_in_other_processes(sb, orc):
 def _residual_identity(sb, f, obs, y, sub, sigma2):
     """Size-independent check of the whole pipeline at full BASELINE sizes:
     (K + s2 I) alpha = delta  =>  K[sub, :] alpha = delta[sub] - s2 alpha[sub], where the left side
-    is the posterior mean evaluated AT a subset of the training inputs (zero-mean prior)."""
+    is the posterior mean evaluated AT a subset of the training inputs (zero-mean prior).
+    Also: logpdf's quadratic form |L^{-1} delta|^2 must equal delta' alpha (two different sweeps),
+    i.e. logpdf == -(N log 2pi + logdet + y'alpha)/2 with the handle's own logdet."""
     fx = f(obs, sigma2)
     post = sb.posterior(fx, y)
     alpha = post.alpha
@@ -238,8 +240,56 @@ def _residual_identity(sb, f, obs, y, sub, sigma2):
     rhs = y[sub["idx"]] - sigma2 * alpha[sub["idx"]]
     np.testing.assert_allclose(m, rhs, rtol=0, atol=1e-9 * max(1.0, np.abs(y).max()))
     lp = sb.logpdf(fx, y)
-    assert np.isfinite(lp)
+    ld = fx.factor().logdet()
+    n = len(y)
+    lp2 = -(n * np.log(2 * np.pi) + ld + float(y @ alpha)) / 2
+    assert abs(lp - lp2) <= 1e-11 * abs(lp), (lp, lp2)
+    # bounds: lambda_min >= s2, and Hadamard: logdet <= sum log diag(K + s2 I)
+    assert n * np.log(sigma2) < ld <= float(np.sum(np.log(sb.var(fx)))) + 1e-9 * n
     return lp
+
+
+@pytest.mark.parametrize("n", [16384, 32768])
+def test_config2_oracle_parity_large(sb, n):
+    """Config-2 inputs (bench.make_inputs) against the CPU oracle fast path at N = 16384 / 32768:
+    logpdf, posterior mean and variance to rtol 1e-10 (north_star tolerance)."""
+    import os
+    import bench
+    if n > 16384:
+        import psutil
+        if psutil.virtual_memory().available < 60e9 or (os.cpu_count() or 1) < 16:
+            pytest.skip("host too small for the N=32768 CPU oracle (needs ~35 GB, >= 16 threads)")
+    ns = 512
+    x, y, xs = bench.make_inputs(n, ns)
+    lpo, mo, vo, _ = bench.cpu_pipeline(x, y, xs, bench.SIGMA2)
+    f = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel())))
+    fx = f(sb.GPPPInput("f", x), bench.SIGMA2)
+    lp = sb.logpdf(fx, y)
+    m, v = sb.mean_and_var(sb.posterior(fx, y), sb.GPPPInput("f", xs))
+    assert abs(lp - lpo) <= RTOL * abs(lpo), (lp, lpo)
+    np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(v, vo, rtol=RTOL, atol=1e-11)
+
+
+def test_config3_oracle_parity_3x4096(sb, orc):
+    """Config-3 shape (GPPP f3 = f1 + f2 over BlockData) at 3 x 4096 against the oracle's
+    recursive routing + LAPACK: logpdf, posterior mean/var of all three processes."""
+    rng = np.random.default_rng(123456)
+    fs, fo = both(sb, orc, f3_model)
+    names = ["f1", "f2", "f3"]
+    xs = [rng.uniform(0, 128, 4096) for _ in range(3)]
+    xt = [rng.uniform(0, 128, 200) for _ in range(3)]
+    bs = sb.BlockData(*[sb.GPPPInput(nm, v) for nm, v in zip(names, xs)])
+    bo = orc.BlockData(*[orc.GPPPInput(nm, v) for nm, v in zip(names, xs)])
+    ts = sb.BlockData(*[sb.GPPPInput(nm, v) for nm, v in zip(names, xt)])
+    to = orc.BlockData(*[orc.GPPPInput(nm, v) for nm, v in zip(names, xt)])
+    y = np.concatenate([np.sin(v) for v in xs]) + 0.3 * rng.standard_normal(3 * 4096)
+    lp, lpo = sb.logpdf(fs(bs, 0.1), y), orc.logpdf(fo(bo, 0.1), y)
+    assert abs(lp - lpo) <= RTOL * abs(lpo), (lp, lpo)
+    m, v = sb.mean_and_var(sb.posterior(fs(bs, 0.1), y), ts)
+    mo, vo = orc.mean_and_var(orc.posterior(fo(bo, 0.1), y), to)
+    np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(v, vo, rtol=RTOL, atol=1e-11)
 
 
 def test_config2_full_size_properties(sb):
@@ -250,8 +300,6 @@ def test_config2_full_size_properties(sb):
     f = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel())))
     idx = np.arange(0, n, 173)
     lp = _residual_identity(sb, f, sb.GPPPInput("f", x), y, dict(idx=idx, inputs=sb.GPPPInput("f", x[idx])), 0.1)
-    # logdet bounds for K + s2 I with unit-variance kernel: n log s2 <= logdet <= n log(1 + s2) (Hadamard)
-    ld = f(sb.GPPPInput("f", x), 0.1).factor().logdet() if False else None
     assert -1e6 < lp < 0
 
 
@@ -328,3 +376,81 @@ def test_nested_gppp_on_device(sb, orc):
     np.testing.assert_allclose(sb.cov(fs, a_s, b_s), orc.cov(fo, a_o, b_o), rtol=1e-13, atol=1e-14)
     y = rng.standard_normal(50)
     np.testing.assert_allclose(sb.logpdf(fs(a_s, 0.1), y), orc.logpdf(fo(a_o, 0.1), y), rtol=RTOL)
+
+
+def test_two_posteriors_share_one_factor(sb, orc):
+    """posterior is a pure function (AbstractGPs PosteriorGP owns its alpha): a second
+    posterior(fx, y2) must not change what the first one predicts."""
+    rng = np.random.default_rng(21)
+    n = 700
+    x, xs = rng.uniform(0, 20, n), rng.uniform(0, 20, 90)
+    y1 = np.sin(x) + 0.3 * rng.standard_normal(n)
+    y2 = np.cos(2 * x) + 0.3 * rng.standard_normal(n)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    fxs, fxo = fs(sb.GPPPInput("f", x), 0.1), fo(orc.GPPPInput("f", x), 0.1)
+    p1, p2 = sb.posterior(fxs, y1), sb.posterior(fxs, y2)
+    o1, o2 = orc.posterior(fxo, y1), orc.posterior(fxo, y2)
+    xi_s, xi_o = sb.GPPPInput("f", xs), orc.GPPPInput("f", xs)
+    for p, o in [(p1, o1), (p2, o2), (p1, o1)]:  # interleaved: alpha is re-installed on demand
+        np.testing.assert_allclose(sb.mean(p, xi_s), orc.mean(o, xi_o), rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(p1.alpha, o1.alpha, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(p2.alpha, o2.alpha, rtol=1e-9, atol=1e-11)
+
+
+def test_posterior_cross_cov_and_dense_post_noise(sb, orc):
+    """cov(f_post, x, z) with x != z (AbstractGPs App. A) and rand/logpdf of f_post(x*, Sigma_dense)."""
+    rng = np.random.default_rng(22)
+    fs, fo = both(sb, orc, f3_model)
+    xtr = [rng.uniform(0, 10, k) for k in (150, 120, 90)]
+    bs = sb.BlockData(*[sb.GPPPInput(nm, v) for nm, v in zip(["f1", "f2", "f3"], xtr)])
+    bo = orc.BlockData(*[orc.GPPPInput(nm, v) for nm, v in zip(["f1", "f2", "f3"], xtr)])
+    y = orc.rand(fo(bo, 0.1), rng.standard_normal(360))
+    ps, po = sb.posterior(fs(bs, 0.1), y), orc.posterior(fo(bo, 0.1), y)
+    xa, xb = rng.uniform(0, 10, 41), rng.uniform(0, 10, 57)
+    K = sb.cov(ps, sb.GPPPInput("f3", xa), sb.GPPPInput("f1", xb))
+    Ko = orc.cov(po, orc.GPPPInput("f3", xa), orc.GPPPInput("f1", xb))
+    assert K.shape == (41, 57)
+    np.testing.assert_allclose(K, Ko, rtol=1e-9, atol=1e-11)
+    # dense observation noise on the posterior FiniteGP
+    A = rng.standard_normal((41, 41))
+    S = 0.05 * (A @ A.T) / 41 + 0.1 * np.eye(41)
+    z = rng.standard_normal(41)
+    fps, fpo = ps(sb.GPPPInput("f3", xa), S), po(orc.GPPPInput("f3", xa), S)
+    ys = orc.rand(fpo, z)
+    np.testing.assert_allclose(sb.rand(fps, z), ys, rtol=1e-8, atol=1e-9)
+    lp, lpo = sb.logpdf(fps, ys), orc.logpdf(fpo, ys)
+    assert abs(lp - lpo) <= 1e-9 * abs(lpo)
+
+
+def test_posterior_of_posterior(sb, orc):
+    """posterior(f_post(x2, s2), y2) == conditioning the prior on the stacked observations."""
+    rng = np.random.default_rng(23)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.Matern52Kernel()))), orc.gppp(lambda GP: dict(f=GP(orc.Matern52Kernel())))
+    x1, x2, xs = rng.uniform(0, 10, 200), rng.uniform(0, 10, 130), rng.uniform(0, 10, 50)
+    y1, y2 = np.sin(x1), np.sin(x2) + 0.1
+    p1 = sb.posterior(fs(sb.GPPPInput("f", x1), 0.1), y1)
+    p12 = sb.posterior(p1(sb.GPPPInput("f", x2), 0.2), y2)
+    bo = orc.BlockData(orc.GPPPInput("f", x1), orc.GPPPInput("f", x2))
+    noise = np.concatenate([np.full(200, 0.1), np.full(130, 0.2)])
+    po = orc.posterior(fo(bo, noise), np.concatenate([y1, y2]))
+    m, v = sb.mean_and_var(p12, sb.GPPPInput("f", xs))
+    mo, vo = orc.mean_and_var(po, orc.GPPPInput("f", xs))
+    np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(v, vo, rtol=1e-9, atol=1e-11)
+
+
+def test_vfe_approx_posterior_cov(sb, orc):
+    rng = np.random.default_rng(24)
+    n, m = 1500, 260
+    x = np.sort(rng.uniform(0, 30, n))
+    z = np.linspace(0, 30, m)
+    y = np.sin(x) + 0.2 * rng.standard_normal(n)
+    xs, xz = rng.uniform(0, 30, 70), rng.uniform(0, 30, 33)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    aps = sb.approx_posterior(sb.VFE(fs(sb.GPPPInput("f", z), 1e-9)), fs(sb.GPPPInput("f", x), 0.1), y)
+    apo = orc.vfe_posterior(orc.VFE(fo(orc.GPPPInput("f", z), 1e-9)), fo(orc.GPPPInput("f", x), 0.1), y)
+    K, Ko = sb.cov(aps, sb.GPPPInput("f", xs)), orc.cov(apo, orc.GPPPInput("f", xs))
+    np.testing.assert_allclose(K, Ko, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(np.diag(K), sb.var(aps, sb.GPPPInput("f", xs)), rtol=1e-7, atol=1e-9)
+    Kx = sb.cov(aps, sb.GPPPInput("f", xs), sb.GPPPInput("f", xz))
+    np.testing.assert_allclose(Kx, orc.cov(apo, orc.GPPPInput("f", xs), orc.GPPPInput("f", xz)), rtol=1e-7, atol=1e-9)
