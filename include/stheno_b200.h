@@ -129,6 +129,7 @@ typedef struct {
     double trailing_kernel_ms; /* sum of per-launch CUDA-event durations of that kernel */
     int64_t trailing_launches;
     int64_t kernel_launches; /* all kernels launched by this library since last reset */
+    double trailing_int8_ops; /* int8 tensor-core ops (2 * MACs) issued by the tcgen05 trailing kernel; 0 on the DMMA path */
 } sb_timings;
 
 typedef struct sb_ctx sb_ctx;
@@ -147,6 +148,9 @@ int32_t sb_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const vo
                            sb_ctx** out);
 int32_t sb_ctx_destroy(sb_ctx* ctx);
 int32_t sb_ctx_timings(sb_ctx* ctx, sb_timings* out, int32_t reset);
+/* options: "trailing" = 0 fp64 DMMA (mma.sync) | 1 tcgen05 int8 Ozaki slices fed from TMEM (also env
+ * SB_TRAILING=dmma|ozaki at context creation); "fine_timing" = 0 | 1. */
+int32_t sb_ctx_set_option(sb_ctx* ctx, const char* key, int64_t value);
 /* benchmark support: record a CUDA event on the library's stream into slot 0..7 / read the
  * elapsed device time between two recorded slots (synchronises on the later one). */
 int32_t sb_ctx_mark(sb_ctx* ctx, int32_t slot);

@@ -29,6 +29,10 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 using namespace sb;
 
+#ifndef SB_DEFAULT_TRAILING
+#define SB_DEFAULT_TRAILING 0
+#endif
+
 // NCCL is bound lazily with dlopen (only when world > 1): a single-GPU / Julia user never loads
 // it, and inside a Python process that also imports torch the already-loaded libnccl.so.2
 // (torch bundles its own) is reused instead of clashing with the system copy.
@@ -87,6 +91,7 @@ struct sb_ctx {
     cudaStream_t stream2 = nullptr;  // look-ahead panel stream (multi-GPU)
     sb_timings tm{};
     bool fine_timing = true;
+    int trailing_mode = 0;   // 0: fp64 DMMA (mma.sync), 1: tcgen05 int8 Ozaki slices (ozaki.cu)
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // caching device allocator: the factor (17 GB at N=65536) and the posterior workspace are
     // re-used across calls instead of paying cudaMalloc/cudaFree (both device-synchronising)
@@ -150,6 +155,15 @@ struct sb_factor {
     bool has_alpha = false;
     double logdet = 0.0;
     size_t bytes_L = 0, bytes_invL = 0, bytes_ld = 0, bytes_panel = 0, bytes_alpha = 0, bytes_ldiag = 0;
+    // tcgen05 trailing update (ozaki.cu): two sets (look-ahead) of int8 digit planes + row scales
+    bool oz = false;
+    signed char* oz_planes[2] = {nullptr, nullptr};
+    double* oz_scale[2] = {nullptr, nullptr};
+    int* oz_expo[2] = {nullptr, nullptr};
+    const double** oz_pt_dev = nullptr;  // device array [2][OUTER_BLOCKS] of tiled-panel base pointers
+    OzMaps oz_maps[2];
+    OzDesc oz_desc;
+    size_t bytes_oz_planes = 0;
 };
 
 namespace {
@@ -404,6 +418,7 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
     {
         const int nq0 = (int)(nblk < OUTER_BLOCKS ? nblk : OUTER_BLOCKS);
         SB_TRY(panel_phase(c, f, 0, nq0, Pw[0], Pt[0], rank, world, s2, &comm_ev));
+        if (f->oz) launch_oz_slice(f->oz_pt_dev, nq0, 0, Np, f->oz_scale[0], f->oz_expo[0], f->oz_planes[0], s2);
         SB_CUDA(cudaEventRecord(ev_p[0], s2));
     }
     double flops = 0;
@@ -417,15 +432,30 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
         SB_CUDA(cudaEventRecord(ev_t0[s], s1));
         if (jt < nblk) {
             const int64_t jA = jt + OUTER_BLOCKS < nblk ? jt + OUTER_BLOCKS : nblk;
-            launch_syrk_packed(f->L, k0, Pt[set], nq, jt, jA, rank, world, s1);            // T^A: next panels' columns
+            auto trailing = [&](int64_t jlo, int64_t jhi, int reserve) -> int32_t {
+                if (f->oz) {
+                    if (launch_syrk_ozaki(f->L, k0, nq, jlo, jhi, rank, world, &f->oz_maps[set], f->oz_scale[set],
+                                          &f->oz_desc, 0, s1, reserve) != 0) {
+                        sb::set_error("tcgen05 trailing kernel could not be launched");
+                        return SB_ERR_CUDA;
+                    }
+                } else {
+                    launch_syrk_packed(f->L, k0, Pt[set], nq, jlo, jhi, rank, world, s1, reserve);
+                }
+                return SB_OK;
+            };
+            SB_TRY(trailing(jt, jA, 0));                                                   // T^A: next panels' columns
             SB_CUDA(cudaEventRecord(ev_a[s], s1));
             if (s + 1 < nsteps) {
                 const int nq1 = (int)(nblk - jt < OUTER_BLOCKS ? nblk - jt : OUTER_BLOCKS);
                 SB_CUDA(cudaStreamWaitEvent(s2, ev_a[s], 0));
                 SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2, &comm_ev));
+                if (f->oz)
+                    launch_oz_slice(f->oz_pt_dev + (set ^ 1) * OUTER_BLOCKS, nq1, jt, Np, f->oz_scale[set ^ 1],
+                                    f->oz_expo[set ^ 1], f->oz_planes[set ^ 1], s2);
                 SB_CUDA(cudaEventRecord(ev_p[s + 1], s2));
             }
-            if (jA < nblk) launch_syrk_packed(f->L, k0, Pt[set], nq, jA, nblk, rank, world, s1, LOOKAHEAD_SMS);  // T^B
+            if (jA < nblk) SB_TRY(trailing(jA, nblk, LOOKAHEAD_SMS));                      // T^B
             int64_t tiles = syrk_packed_tiles(nblk, k0, jt, nblk, rank, world);
             if (tiles > 0) { flops += (double)tiles * 2.0 * NB * NB * ((double)nq * NB); nlaunch++; }
         }
@@ -455,6 +485,7 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
     }
     c->tm.trailing_flops += flops;
     c->tm.trailing_launches += nlaunch;
+    if (f->oz) c->tm.trailing_int8_ops += 28.0 * flops;
     return SB_OK;
 }
 
@@ -465,8 +496,12 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     const int world = force_local ? 1 : c->world, rank = force_local ? 0 : c->rank;
     // look-ahead (panel phase of step s+1 on stream 2 under the big trailing update of step s) also
     // pays on ONE GPU: the serial potrf/TRSM chain (106 ms at N=65536) leaves the critical path
+    // (measured, round 2: with the DMMA trailing kernel on ONE GPU the 8 SMs the look-ahead reserves
+    //  cost as much as the hidden 106 ms panel chain saves, so it is used for world > 1 and for the
+    //  3x faster tcgen05 trailing kernel, where the serial panel chain would be ~10 % of the step)
     static const bool no_la = getenv("SB_NO_LOOKAHEAD") != nullptr;
-    if (!no_la && nblk > OUTER_BLOCKS) {
+    static const bool force_la = getenv("SB_FORCE_LOOKAHEAD") != nullptr;
+    if (!no_la && nblk > OUTER_BLOCKS && (world > 1 || f->oz || force_la)) {
         SB_TRY(cholesky_lookahead(c, f, world, rank));
         if (world > 1) {
             SB_TRY(sync_info(c, f));
@@ -622,6 +657,10 @@ int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     const char* ft = getenv("SB_FINE_TIMING");
     if (ft && ft[0] == '0') c->fine_timing = false;
+    const char* tr = getenv("SB_TRAILING");   // "dmma" | "ozaki"
+    c->trailing_mode = SB_DEFAULT_TRAILING;
+    if (tr && !strcmp(tr, "dmma")) c->trailing_mode = 0;
+    if (tr && !strcmp(tr, "ozaki")) c->trailing_mode = 1;
     *out = c;
     return SB_OK;
 }
@@ -671,6 +710,18 @@ int32_t sb_ctx_timings(sb_ctx* c, sb_timings* out, int32_t reset) {
     if (out) *out = c->tm;
     if (reset) c->tm = sb_timings{};
     return SB_OK;
+}
+
+int32_t sb_ctx_set_option(sb_ctx* c, const char* key, int64_t value) {
+    SB_CHECK(c && key, "null argument");
+    if (!strcmp(key, "trailing")) {
+        SB_CHECK(value == 0 || value == 1, "trailing: 0 = fp64 DMMA, 1 = tcgen05 int8 Ozaki");
+        c->trailing_mode = (int)value;
+        return SB_OK;
+    }
+    if (!strcmp(key, "fine_timing")) { c->fine_timing = value != 0; return SB_OK; }
+    sb::set_error(std::string("unknown option ") + key);
+    return SB_ERR_INVALID;
 }
 
 int32_t sb_owner_of_block(int64_t J, int32_t world) { return world > 0 ? (int32_t)(J % world) : 0; }
@@ -752,6 +803,12 @@ int32_t sb_factor_destroy(sb_factor* f) {
     c->pool_release(f->info_dev, 8);
     c->pool_release(f->panel, f->bytes_panel);
     c->pool_release(f->alpha, f->bytes_alpha);
+    for (int i = 0; i < 2; i++) {
+        c->pool_release(f->oz_planes[i], f->bytes_oz_planes);
+        c->pool_release(f->oz_scale[i], (size_t)f->Np * sizeof(double));
+        c->pool_release(f->oz_expo[i], (size_t)f->Np * sizeof(int));
+    }
+    c->pool_release(f->oz_pt_dev, 2 * OUTER_BLOCKS * sizeof(double*));
     delete f;
     return SB_OK;
 }
@@ -788,6 +845,31 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->alpha, f->bytes_alpha);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream);
+    // tcgen05 path: worth it (and exercised) once the trailing matrix has a few hundred tiles
+    if (e == cudaSuccess && c->trailing_mode == 1 && nblk > 2 * OUTER_BLOCKS) {
+        f->bytes_oz_planes = oz_planes_bytes(f->Np);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = c->pool_alloc((void**)&f->oz_planes[i], f->bytes_oz_planes);
+            if (e == cudaSuccess) e = c->pool_alloc((void**)&f->oz_scale[i], (size_t)f->Np * sizeof(double));
+            if (e == cudaSuccess) e = c->pool_alloc((void**)&f->oz_expo[i], (size_t)f->Np * sizeof(int));
+        }
+        if (e == cudaSuccess) e = c->pool_alloc((void**)&f->oz_pt_dev, 2 * OUTER_BLOCKS * sizeof(double*));
+        if (e == cudaSuccess) {
+            const double* hp[2 * OUTER_BLOCKS];
+            for (int i = 0; i < 2 * OUTER_BLOCKS; i++) hp[i] = f->panel + (int64_t)i * tiled_panel_elems(f->Np);
+            e = cudaMemcpy(f->oz_pt_dev, hp, sizeof(hp), cudaMemcpyHostToDevice);
+        }
+        if (e == cudaSuccess) {
+            oz_default_desc(&f->oz_desc, 0);
+            if (oz_make_maps(f->oz_planes[0], f->Np, 0, &f->oz_maps[0]) != 0 ||
+                oz_make_maps(f->oz_planes[1], f->Np, 0, &f->oz_maps[1]) != 0) {
+                sb_factor_destroy(f);
+                sb::set_error("cuTensorMapEncodeTiled failed for the int8 digit planes");
+                return SB_ERR_CUDA;
+            }
+            f->oz = true;
+        }
+    }
     if (e != cudaSuccess) {
         sb_factor_destroy(f);
         return sb::cuda_fail(e, "factor_alloc", __FILE__, __LINE__);

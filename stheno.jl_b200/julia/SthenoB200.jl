@@ -428,7 +428,7 @@ end
 struct SbTimings
     assemble_ms::Float64; panel_ms::Float64; trailing_ms::Float64; solve_ms::Float64; predict_ms::Float64
     comm_ms::Float64; total_ms::Float64; trailing_flops::Float64; trailing_kernel_ms::Float64
-    trailing_launches::Int64; kernel_launches::Int64
+    trailing_launches::Int64; kernel_launches::Int64; trailing_int8_ops::Float64
 end
 function timings(; reset::Bool=false)
     t = Ref{SbTimings}()
@@ -436,6 +436,10 @@ function timings(; reset::Bool=false)
     t[]
 end
 
-export b200, B200GPPP, timings
+# "trailing" => 0 (fp64 DMMA) | 1 (tcgen05 int8 Ozaki slices)
+set_option!(key::AbstractString, value::Integer) =
+    check(ccall((:sb_ctx_set_option, LIB), Int32, (Ptr{Cvoid}, Cstring, Int64), ctx().h, key, value))
+
+export b200, B200GPPP, timings, set_option!
 
 end # module

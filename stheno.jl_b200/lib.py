@@ -44,7 +44,7 @@ class sb_timings(C.Structure):
                 ("solve_ms", C.c_double), ("predict_ms", C.c_double), ("comm_ms", C.c_double),
                 ("total_ms", C.c_double), ("trailing_flops", C.c_double),
                 ("trailing_kernel_ms", C.c_double), ("trailing_launches", C.c_int64),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("trailing_int8_ops", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -52,7 +52,7 @@ class sb_timings(C.Structure):
 
 EXPORTS = [
     "sb_abi_version", "sb_last_error", "sb_ctx_create", "sb_nccl_unique_id", "sb_ctx_create_dist",
-    "sb_ctx_destroy", "sb_ctx_timings", "sb_ctx_mark", "sb_ctx_elapsed_ms", "sb_owner_of_block",
+    "sb_ctx_destroy", "sb_ctx_timings", "sb_ctx_set_option", "sb_ctx_mark", "sb_ctx_elapsed_ms", "sb_owner_of_block",
     "sb_owned_trailing_tiles", "sb_row_chunk", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
     "sb_factor_destroy", "sb_factor_logdet", "sb_logpdf", "sb_factor_set_data", "sb_factor_alpha",
     "sb_factor_set_alpha", "sb_predict", "sb_predict_cov", "sb_predict_factor", "sb_rand", "sb_factor_get_L",
@@ -96,6 +96,7 @@ def load():
         "sb_ctx_create_dist": [i32, i32, i32, vp, P(vp)],
         "sb_ctx_destroy": [vp],
         "sb_ctx_timings": [vp, P(sb_timings), i32],
+        "sb_ctx_set_option": [vp, C.c_char_p, i64],
         "sb_ctx_mark": [vp, i32],
         "sb_ctx_elapsed_ms": [vp, i32, i32, P(C.c_double)],
         "sb_cov_dense": [vp, P(sb_covspec), vp],
@@ -172,6 +173,10 @@ class Context:
         t = sb_timings()
         check(load().sb_ctx_timings(self.h, C.byref(t), 1 if reset else 0))
         return t.asdict()
+
+    def set_option(self, key: str, value: int):
+        """"trailing": 0 = fp64 DMMA, 1 = tcgen05 int8 Ozaki trailing update; "fine_timing": 0/1."""
+        check(load().sb_ctx_set_option(self.h, key.encode(), int(value)))
 
     def mark(self, slot):
         check(load().sb_ctx_mark(self.h, slot))

@@ -454,3 +454,54 @@ def test_vfe_approx_posterior_cov(sb, orc):
     np.testing.assert_allclose(np.diag(K), sb.var(aps, sb.GPPPInput("f", xs)), rtol=1e-7, atol=1e-9)
     Kx = sb.cov(aps, sb.GPPPInput("f", xs), sb.GPPPInput("f", xz))
     np.testing.assert_allclose(Kx, orc.cov(apo, orc.GPPPInput("f", xs), orc.GPPPInput("f", xz)), rtol=1e-7, atol=1e-9)
+
+
+@pytest.fixture
+def ozaki_ctx(sb):
+    """Route the trailing updates of the default context through the tcgen05 int8-Ozaki kernel."""
+    ctx = sb.default_context()
+    ctx.set_option("trailing", 1)
+    try:
+        yield ctx
+    finally:
+        ctx.set_option("trailing", int(__import__("os").environ.get("SB_TEST_DEFAULT_TRAILING", "0")))
+
+
+@pytest.mark.parametrize("n", [2500, 4096])
+def test_tcgen05_ozaki_trailing_update_parity(sb, orc, ozaki_ctx, n):
+    """fp64 Cholesky whose trailing SYRK runs as 28 int8 tcgen05 MMAs per fp64 MMA (ozaki.cu):
+    the factor must agree with LAPACK to 1e-12 and logpdf / posterior with the oracle to 1e-10."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(41)
+    x, xs = rng.uniform(0, n / 32, n), rng.uniform(0, n / 32, 300)
+    y = np.sin(x) + 0.3 * rng.standard_normal(n)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    fxs, fxo = fs(sb.GPPPInput("f", x), 0.1), fo(orc.GPPPInput("f", x), 0.1)
+    t0 = ozaki_ctx.timings(reset=True)
+    lp, lpo = sb.logpdf(fxs, y), orc.logpdf(fxo, y)
+    tm = ozaki_ctx.timings()
+    assert tm["trailing_int8_ops"] > 0, "the tcgen05 path did not run"
+    assert abs(lp - lpo) <= RTOL * abs(lpo), (lp, lpo)
+    L = fxs.factor().to_dense_L()
+    Lref = sla.cholesky(orc.cov(fxo), lower=True)
+    np.testing.assert_allclose(L, Lref, rtol=0, atol=1e-12)
+    m, v = sb.mean_and_var(sb.posterior(fxs, y), sb.GPPPInput("f", xs))
+    mo, vo = orc.mean_and_var(orc.posterior(fxo, y), orc.GPPPInput("f", xs))
+    np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(v, vo, rtol=RTOL, atol=1e-11)
+
+
+def test_tcgen05_ozaki_gppp_badly_scaled_rows(sb, orc, ozaki_ctx):
+    """Rows of very different magnitude (function-scaled processes, heteroscedastic noise): the per-row
+    power-of-two scaling of the digit planes must keep fp64-level accuracy."""
+    rng = np.random.default_rng(42)
+    fs, fo = both(sb, orc, rich_model)
+    names = ["g1", "g4", "g3"]
+    xs = [rng.uniform(-3, 3, k) for k in (900, 700, 800)]
+    bs = sb.BlockData(*[sb.GPPPInput(nm, v) for nm, v in zip(names, xs)])
+    bo = orc.BlockData(*[orc.GPPPInput(nm, v) for nm, v in zip(names, xs)])
+    noise = 10.0 ** rng.uniform(-4, 0, 2400)
+    y = orc.rand(fo(bo, noise), rng.standard_normal(2400))
+    lp, lpo = sb.logpdf(fs(bs, noise), y), orc.logpdf(fo(bo, noise), y)
+    assert ozaki_ctx.timings()["trailing_int8_ops"] > 0
+    assert abs(lp - lpo) <= 1e-9 * abs(lpo), (lp, lpo)
