@@ -30,6 +30,7 @@ import numpy as np  # noqa: E402
 N_TRAIN = 65536
 N_TEST = 4096
 SIGMA2 = 0.1
+DEFAULT_TRAILING = "dmma"
 DMMA_PEAK_TFLOPS = 37.1  # builder-measured, tools/mb_fp64_peak.cu on this pool's B200 (profiles/)
 
 
@@ -231,6 +232,7 @@ def gpu_main(args):
         ctx = sblib.Context(local)
     sblib.set_default_context(ctx)
     lib = sblib.load()
+    ctx.set_option("trailing", 1 if args.trailing == "ozaki" else 0)
 
     n, ns = args.n, args.ns
     x, y, xs = make_inputs(n, ns)
@@ -343,26 +345,46 @@ def gpu_main(args):
         return
     np.testing.assert_allclose(mean_d.cpu().numpy(), m_e, rtol=1e-9, atol=1e-10)
 
-    # ---- roofline of the dominant kernel (DMMA trailing update) ----------------------------------
-    ach = tm["trailing_flops"] / (tm["trailing_kernel_ms"] * 1e-3) / 1e12 if tm["trailing_kernel_ms"] else None
-    roof = {"bound": "tensor", "kernel": "gemm_nt_kernel (fp64 DMMA SYRK trailing update)",
-            "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-            "frac": (ach / DMMA_PEAK_TFLOPS) if ach else None,
-            "peak_source": "builder-measured mma.sync m8n8k4 f64 microbenchmark (tools/mb_fp64_peak.cu, "
-                           "profiles/mb_fp64_peak_r1.txt); MEASURED_PEAKS.json has no fp64 entry, "
-                           "tcgen05 has no fp64 kind",
-            "launches": tm["trailing_launches"] // max(1, args.steps),
-            "flops_per_step": tm["trailing_flops"] / args.steps,
-            # one `ncu --set full` capture of a K=256 trailing launch of an N=32768 factorisation
-            # (profiles/ncu_gemm_nt_r1.txt): dram read 6.97 GB + write 4.35 GB against 8.32 GB
-            # algorithmic (C read + write of 32385 blocks; operand re-reads missing L2 are the excess)
-            "traffic": 11.32e9, "traffic_algorithmic": 8.32e9,
-            "traffic_note": "bytes for ONE captured launch (N=32768, step 0), not the per-step average"}
-    hbm_peak = 6575.8
+    # ---- roofline of the dominant kernel (the trailing update of the Cholesky) -----------------------
+    peaks = {}
     try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = None
+    try:  # per-launch DRAM bytes of the shipped trailing kernel from a committed `ncu --set full` capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.trailing)
+    except Exception:
+        pass
+    t_ms = tm["trailing_kernel_ms"]
+    fp64_tf = tm["trailing_flops"] / (t_ms * 1e-3) / 1e12 if t_ms else None
+    if tm.get("trailing_int8_ops", 0) > 0:
+        # tcgen05 kind::i8: 28 int8 MMAs per fp64 MMA.  Peak = 2 x the MEASURED dense bf16 tensor peak
+        # (int8 runs at twice the bf16 rate on sm_100a); sustained figure: the kernel runs inside a long step.
+        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak = 2.0 * bf16
+        ach = tm["trailing_int8_ops"] / (t_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "ozaki_syrk_kernel (tcgen05.mma kind::i8 from TMEM, fp64 via 7 int8 digit planes)",
+                "achieved": ach, "peak": peak, "unit": "TOP/s (int8)", "frac": ach / peak,
+                "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "2 x fallback 1400 TF (of fallback)"),
+                "fp64_equivalent_tflops": fp64_tf, "vs_dmma_peak": fp64_tf / DMMA_PEAK_TFLOPS if fp64_tf else None,
+                "launches": tm["trailing_launches"] // max(1, args.steps),
+                "flops_per_step": tm["trailing_flops"] / args.steps,
+                "int8_ops_per_step": tm["trailing_int8_ops"] / args.steps}
+    else:
+        roof = {"bound": "tensor", "kernel": "gemm_nt_kernel (fp64 DMMA SYRK trailing update)",
+                "achieved": fp64_tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": (fp64_tf / DMMA_PEAK_TFLOPS) if fp64_tf else None,
+                "peak_source": "builder-measured mma.sync m8n8k4 f64 microbenchmark (tools/mb_fp64_peak.cu, "
+                               "profiles/mb_fp64_peak_r1.txt); MEASURED_PEAKS.json has no fp64 entry, "
+                               "tcgen05 has no fp64 kind",
+                "launches": tm["trailing_launches"] // max(1, args.steps),
+                "flops_per_step": tm["trailing_flops"] / args.steps}
+    roof["traffic"] = traffic["dram_bytes_per_launch"] if traffic else None
+    if traffic:
+        roof["traffic_algorithmic"] = traffic.get("algorithmic_bytes_per_launch")
+        roof["traffic_source"] = traffic.get("source")
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     asm_bytes = (n * (n + 1) / 2 * 8 + n * 8)
     roof_asm = {"bound": "hbm", "kernel": "assemble_kernel<packed>", "achieved": asm_bytes / (tm["assemble_ms"] / args.steps * 1e-3) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s"}
@@ -386,6 +408,7 @@ def gpu_main(args):
         "config": {"workload": f"config 2: SEKernel GP N={n} fp64, 1-D inputs U(0,N/32), sigma2=0.1: "
                                f"kernelmatrix + Cholesky logpdf + posterior mean/var at N*={ns}",
                    "n_train": n, "n_test": ns, "l2": "inputs >> L2 (17.2 GB factor; no flush needed)",
+                   "trailing": args.trailing,
                    "parallelism": f"1-D block-cyclic columns x{args.gpus}, NCCL panel broadcast" if args.gpus > 1 else "single GPU"},
         "e2e": {"value": n / e2e_s, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3},
@@ -439,6 +462,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_TRAIN)
     ap.add_argument("--ns", type=int, default=N_TEST)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--trailing", default=os.environ.get("SB_BENCH_TRAILING", DEFAULT_TRAILING), choices=["dmma", "ozaki"],
+                    help="Cholesky trailing update: fp64 DMMA (mma.sync) or tcgen05 int8 Ozaki slices")
     args = ap.parse_args()
     global _OUT_FD
     sys.stdout.flush()

@@ -213,6 +213,23 @@ int32_t sb_rand(sb_ctx* ctx, sb_factor* f, const void* z, int32_t S, void* out);
  * factorised on the device; the returned handle works with sb_rand / sb_logpdf / sb_factor_logdet. */
 int32_t sb_predict_factor(sb_ctx* ctx, sb_factor* f, const sb_covspec* cross, const sb_covspec* prior_full,
                           const sb_noise* noise, sb_factor** out, int64_t* info);
+/* sb_logpdf_grad replaces the reverse-mode pass through logpdf(fx, y) (Zygote + the ChainRules
+ * glue of src/affine_transformations/cross.jl:8-22; examples/getting_started/script.jl:154-213):
+ *   dlogpdf/dtheta = 1/2 tr((alpha alpha' - K^{-1}) dK/dtheta)
+ * spec = the symmetric spec the factor was built from; sb_factor_set_data(delta) must have been
+ * called.  g_terms[2t] = d/d coeff_t, g_terms[2t+1] = d/d log(s_t) where the term's inputs are
+ * z = s_t x (lengthscale derivative; 0 for White / Constant).  g_noise_diag[i] = 1/2 (alpha_i^2 -
+ * (K^{-1})_ii) = d/d Sigma_y[i,i]  (scalar noise: sum them).  The host applies the chain rule to its
+ * own hyper-parameters (kernel variance multiplies coeff, 1/lengthscale is s). */
+int32_t sb_logpdf_grad(sb_ctx* ctx, sb_factor* f, const sb_covspec* spec, double* g_terms,
+                       void* g_noise_diag);
+/* Factor checkpoint (the reference's PosteriorGP is a plain serialisable struct
+ * (alpha, C, x, delta)): sb_factor_export writes header | packed L | diagonal-block inverses | alpha
+ * into a caller buffer (host or device) of sb_factor_export_size bytes; sb_factor_import rebuilds a
+ * handle that behaves exactly like the original (logpdf / predict / rand, bit-identical). */
+int32_t sb_factor_export_size(sb_ctx* ctx, sb_factor* f, int64_t* nbytes);
+int32_t sb_factor_export(sb_ctx* ctx, sb_factor* f, void* blob, int64_t nbytes);
+int32_t sb_factor_import(sb_ctx* ctx, const void* blob, int64_t nbytes, sb_factor** out);
 /* debug / parity: copy the lower-triangular factor out as a dense column-major N x N matrix */
 int32_t sb_factor_get_L(sb_ctx* ctx, sb_factor* f, void* L_out);
 

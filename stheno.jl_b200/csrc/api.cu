@@ -32,6 +32,9 @@ using namespace sb;
 #ifndef SB_DEFAULT_TRAILING
 #define SB_DEFAULT_TRAILING 0
 #endif
+#ifndef SB_DEFAULT_OZ_MODE
+#define SB_DEFAULT_OZ_MODE 0
+#endif
 
 // NCCL is bound lazily with dlopen (only when world > 1): a single-GPU / Julia user never loads
 // it, and inside a Python process that also imports torch the already-loaded libnccl.so.2
@@ -92,6 +95,9 @@ struct sb_ctx {
     sb_timings tm{};
     bool fine_timing = true;
     int trailing_mode = 0;   // 0: fp64 DMMA (mma.sync), 1: tcgen05 int8 Ozaki slices (ozaki.cu)
+    int num_sms = 148;
+    int oz_mode = SB_DEFAULT_OZ_MODE;  // SB_OZ_MODE=0|2
+    bool legacy_solve = false;  // SB_SOLVE=legacy: two launches per block instead of the persistent sweep
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // caching device allocator: the factor (17 GB at N=65536) and the posterior workspace are
     // re-used across calls instead of paying cudaMalloc/cudaFree (both device-synchronising)
@@ -160,9 +166,10 @@ struct sb_factor {
     signed char* oz_planes[2] = {nullptr, nullptr};
     double* oz_scale[2] = {nullptr, nullptr};
     int* oz_expo[2] = {nullptr, nullptr};
-    const double** oz_pt_dev = nullptr;  // device array [2][OUTER_BLOCKS] of tiled-panel base pointers
+    unsigned* sweep_flags = nullptr;     // 2*nblk flags of the persistent triangular sweep
     OzMaps oz_maps[2];
     OzDesc oz_desc;
+    int oz_mode = 0;   // TMA / pipeline variant of the tcgen05 kernel (ozaki.cu: 0 = SW64 x 2 stages, 2 = SW32 x 5 stages)
     size_t bytes_oz_planes = 0;
 };
 
@@ -260,6 +267,7 @@ struct DevSpec {
                     SB_CHECK(ZL.dim >= 1 && ZL.dim == ZR.dim, "term: zl/zr dimension mismatch");
                     SB_CHECK(ZL.n == B.nrows && ZR.n == B.ncols, "term: input length != block size");
                     TermDev& D = d.t[t];
+                    d.tix[t] = B.term0 + done + t;
                     D.kernel = T.kernel; D.dim = ZL.dim; D.coeff = T.coeff; D.param = T.param;
                     D.zl = arr[T.zl]; D.zr = arr[T.zr];
                     D.sl = nullptr; D.sr = nullptr;
@@ -418,7 +426,9 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
     {
         const int nq0 = (int)(nblk < OUTER_BLOCKS ? nblk : OUTER_BLOCKS);
         SB_TRY(panel_phase(c, f, 0, nq0, Pw[0], Pt[0], rank, world, s2, &comm_ev));
-        if (f->oz) launch_oz_slice(f->oz_pt_dev, nq0, 0, Np, f->oz_scale[0], f->oz_expo[0], f->oz_planes[0], s2);
+        if (f->oz)
+            launch_oz_slice(oz_src_tiled(Pt[0], nq0), nq0 - 1, nblk - nq0, (int64_t)NB, Np, f->oz_scale[0], f->oz_expo[0],
+                            f->oz_planes[0], s2);
         SB_CUDA(cudaEventRecord(ev_p[0], s2));
     }
     double flops = 0;
@@ -435,7 +445,7 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
             auto trailing = [&](int64_t jlo, int64_t jhi, int reserve) -> int32_t {
                 if (f->oz) {
                     if (launch_syrk_ozaki(f->L, k0, nq, jlo, jhi, rank, world, &f->oz_maps[set], f->oz_scale[set],
-                                          &f->oz_desc, 0, s1, reserve) != 0) {
+                                          &f->oz_desc, f->oz_mode, s1, reserve) != 0) {
                         sb::set_error("tcgen05 trailing kernel could not be launched");
                         return SB_ERR_CUDA;
                     }
@@ -450,9 +460,9 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
                 const int nq1 = (int)(nblk - jt < OUTER_BLOCKS ? nblk - jt : OUTER_BLOCKS);
                 SB_CUDA(cudaStreamWaitEvent(s2, ev_a[s], 0));
                 SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2, &comm_ev));
-                if (f->oz)
-                    launch_oz_slice(f->oz_pt_dev + (set ^ 1) * OUTER_BLOCKS, nq1, jt, Np, f->oz_scale[set ^ 1],
-                                    f->oz_expo[set ^ 1], f->oz_planes[set ^ 1], s2);
+                if (f->oz)  // digit planes of the trailing rows of the panels just factored (block rows >= jt + nq1)
+                    launch_oz_slice(oz_src_tiled(Pt[set ^ 1], nq1), nq1 - 1, nblk - (jt + nq1), (jt + 1) * (int64_t)NB, Np,
+                                    f->oz_scale[set ^ 1], f->oz_expo[set ^ 1], f->oz_planes[set ^ 1], s2);
                 SB_CUDA(cudaEventRecord(ev_p[s + 1], s2));
             }
             if (jA < nblk) SB_TRY(trailing(jA, nblk, LOOKAHEAD_SMS));                      // T^B
@@ -603,6 +613,10 @@ void forward_solve(sb_ctx* c, sb_factor* f, double* b, int S) {
     for (int s0 = 0; s0 < S; s0 += 8) {
         int s = S - s0 < 8 ? S - s0 : 8;
         double* bb = b + (int64_t)s0 * f->Np;
+        if (!c->legacy_solve) {
+            launch_sweep(f->L, f->invL, bb, s, false, f->sweep_flags, c->num_sms, c->stream);
+            continue;
+        }
         for (int64_t k = 0; k < nblk; k++) {
             launch_trsv_diag(f->invL + k * (int64_t)NB * NB, bb + k * NB, f->Np, s, false, c->stream);
             launch_gemv_below(f->L, k, bb, s, c->stream);
@@ -616,6 +630,10 @@ void backward_solve(sb_ctx* c, sb_factor* f, double* b, int S) {
     for (int s0 = 0; s0 < S; s0 += 8) {
         int s = S - s0 < 8 ? S - s0 : 8;
         double* bb = b + (int64_t)s0 * f->Np;
+        if (!c->legacy_solve) {
+            launch_sweep(f->L, f->invL, bb, s, true, f->sweep_flags, c->num_sms, c->stream);
+            continue;
+        }
         for (int64_t k = nblk - 1; k >= 0; k--) {
             launch_gemvT_below(f->L, k, bb, s, c->stream);
             launch_trsv_diag(f->invL + k * (int64_t)NB * NB, bb + k * NB, f->Np, s, true, c->stream);
@@ -657,6 +675,11 @@ int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     const char* ft = getenv("SB_FINE_TIMING");
     if (ft && ft[0] == '0') c->fine_timing = false;
+    SB_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+    const char* om = getenv("SB_OZ_MODE");
+    if (om && (om[0] == '0' || om[0] == '2')) c->oz_mode = om[0] - '0';
+    const char* sv = getenv("SB_SOLVE");
+    c->legacy_solve = sv && !strcmp(sv, "legacy");
     const char* tr = getenv("SB_TRAILING");   // "dmma" | "ozaki"
     c->trailing_mode = SB_DEFAULT_TRAILING;
     if (tr && !strcmp(tr, "dmma")) c->trailing_mode = 0;
@@ -808,7 +831,7 @@ int32_t sb_factor_destroy(sb_factor* f) {
         c->pool_release(f->oz_scale[i], (size_t)f->Np * sizeof(double));
         c->pool_release(f->oz_expo[i], (size_t)f->Np * sizeof(int));
     }
-    c->pool_release(f->oz_pt_dev, 2 * OUTER_BLOCKS * sizeof(double*));
+    c->pool_release(f->sweep_flags, (size_t)2 * (f->Np / NB) * sizeof(unsigned));
     delete f;
     return SB_OK;
 }
@@ -843,6 +866,7 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->info_dev, 8);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->panel, f->bytes_panel);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->alpha, f->bytes_alpha);
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->sweep_flags, (size_t)2 * nblk * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream);
     // tcgen05 path: worth it (and exercised) once the trailing matrix has a few hundred tiles
@@ -853,16 +877,11 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
             if (e == cudaSuccess) e = c->pool_alloc((void**)&f->oz_scale[i], (size_t)f->Np * sizeof(double));
             if (e == cudaSuccess) e = c->pool_alloc((void**)&f->oz_expo[i], (size_t)f->Np * sizeof(int));
         }
-        if (e == cudaSuccess) e = c->pool_alloc((void**)&f->oz_pt_dev, 2 * OUTER_BLOCKS * sizeof(double*));
         if (e == cudaSuccess) {
-            const double* hp[2 * OUTER_BLOCKS];
-            for (int i = 0; i < 2 * OUTER_BLOCKS; i++) hp[i] = f->panel + (int64_t)i * tiled_panel_elems(f->Np);
-            e = cudaMemcpy(f->oz_pt_dev, hp, sizeof(hp), cudaMemcpyHostToDevice);
-        }
-        if (e == cudaSuccess) {
-            oz_default_desc(&f->oz_desc, 0);
-            if (oz_make_maps(f->oz_planes[0], f->Np, 0, &f->oz_maps[0]) != 0 ||
-                oz_make_maps(f->oz_planes[1], f->Np, 0, &f->oz_maps[1]) != 0) {
+            f->oz_mode = c->oz_mode;
+            oz_default_desc(&f->oz_desc, f->oz_mode);
+            if (oz_make_maps(f->oz_planes[0], f->Np, f->oz_mode, &f->oz_maps[0]) != 0 ||
+                oz_make_maps(f->oz_planes[1], f->Np, f->oz_mode, &f->oz_maps[1]) != 0) {
                 sb_factor_destroy(f);
                 sb::set_error("cuTensorMapEncodeTiled failed for the int8 digit planes");
                 return SB_ERR_CUDA;
@@ -962,6 +981,79 @@ static int32_t factor_create_impl(sb_ctx* c, const sb_covspec* spec, const sb_no
 #undef SB_CUDA_F
 }
 
+// ---- factor checkpoint: export / import -------------------------------------------
+// Blob = header | packed L (Np(Np+NB)/2 doubles) | inverses of the diagonal blocks | alpha (Np).
+// PosteriorGP in the reference is a plain struct (alpha, C, x, delta) that Julia can serialise; the
+// device-resident handle gets the same ability here.
+struct FactorBlobHeader {
+    char magic[8];        // "SBFACT01"
+    int64_t N, Np;
+    double logdet;
+    int64_t has_alpha;
+    int64_t reserved[3];
+};
+
+int32_t sb_factor_export_size(sb_ctx* c, sb_factor* f, int64_t* nbytes) {
+    SB_CHECK(c && f && nbytes, "null argument");
+    *nbytes = (int64_t)sizeof(FactorBlobHeader) + (int64_t)f->bytes_L + (int64_t)f->bytes_invL + (int64_t)f->bytes_alpha;
+    return SB_OK;
+}
+
+int32_t sb_factor_export(sb_ctx* c, sb_factor* f, void* blob, int64_t nbytes) {
+    SB_CHECK(c && f && blob, "null argument");
+    int64_t need = 0;
+    sb_factor_export_size(c, f, &need);
+    SB_CHECK(nbytes >= need, "export buffer too small (see sb_factor_export_size)");
+    begin_call(c);
+    FactorBlobHeader h{};
+    memcpy(h.magic, "SBFACT01", 8);
+    h.N = f->N; h.Np = f->Np; h.logdet = f->logdet; h.has_alpha = f->has_alpha ? 1 : 0;
+    char* p = static_cast<char*>(blob);
+    SB_CUDA(cudaMemcpyAsync(p, &h, sizeof(h), cudaMemcpyDefault, c->stream));
+    p += sizeof(h);
+    SB_CUDA(cudaMemcpyAsync(p, f->L.base, f->bytes_L, cudaMemcpyDefault, c->stream));
+    p += f->bytes_L;
+    SB_CUDA(cudaMemcpyAsync(p, f->invL, f->bytes_invL, cudaMemcpyDefault, c->stream));
+    p += f->bytes_invL;
+    SB_CUDA(cudaMemcpyAsync(p, f->alpha, f->bytes_alpha, cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int32_t sb_factor_import(sb_ctx* c, const void* blob, int64_t nbytes, sb_factor** out) {
+    SB_CHECK(c && blob && out, "null argument");
+    SB_CHECK(nbytes >= (int64_t)sizeof(FactorBlobHeader), "blob too small");
+    begin_call(c);
+    *out = nullptr;
+    FactorBlobHeader h{};
+    SB_CUDA(cudaMemcpy(&h, blob, sizeof(h), cudaMemcpyDefault));
+    SB_CHECK(memcmp(h.magic, "SBFACT01", 8) == 0, "not a libstheno_b200 factor blob");
+    SB_CHECK(h.N > 0 && h.Np == round_up(h.N, NB), "corrupt factor blob header");
+    sb_factor* f = nullptr;
+    SB_TRY(factor_alloc(c, h.N, &f));
+    const int64_t need = (int64_t)sizeof(h) + (int64_t)f->bytes_L + (int64_t)f->bytes_invL + (int64_t)f->bytes_alpha;
+    if (nbytes < need) {
+        sb_factor_destroy(f);
+        sb::set_error("factor blob truncated");
+        return SB_ERR_INVALID;
+    }
+    const char* p = static_cast<const char*>(blob) + sizeof(h);
+    cudaError_t e = cudaMemcpyAsync(f->L.base, p, f->bytes_L, cudaMemcpyDefault, c->stream);
+    p += f->bytes_L;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->invL, p, f->bytes_invL, cudaMemcpyDefault, c->stream);
+    p += f->bytes_invL;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->alpha, p, f->bytes_alpha, cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        sb_factor_destroy(f);
+        return sb::cuda_fail(e, "sb_factor_import", __FILE__, __LINE__);
+    }
+    f->logdet = h.logdet;
+    f->has_alpha = h.has_alpha != 0;
+    *out = f;
+    return SB_OK;
+}
+
 int32_t sb_factor_logdet(sb_ctx*, sb_factor* f, double* out) {
     SB_CHECK(f && out, "null argument");
     *out = f->logdet;
@@ -1028,11 +1120,74 @@ int32_t sb_factor_alpha(sb_ctx* c, sb_factor* f, void* alpha_out) {
     return SB_OK;
 }
 
+// workspace of the tcgen05 matrix-TRSM sweep: digit planes / scales / tensor maps of the X panels
+struct OzSweepWs {
+    DevBuf planes, scale, expo;
+    OzMaps maps;
+    int64_t rows = 0;
+    bool ready = false;
+    explicit OzSweepWs(sb_ctx* c) : planes(c), scale(c), expo(c) {}
+    int32_t init(int64_t rows_p, int mode) {
+        rows = rows_p;
+        SB_TRY(planes.alloc(oz_planes_bytes(rows_p)));
+        SB_TRY(scale.alloc(rows_p * sizeof(double)));
+        SB_TRY(expo.alloc(rows_p * sizeof(int)));
+        if (oz_make_maps(reinterpret_cast<signed char*>(planes.p), rows_p, mode, &maps) != 0) {
+            sb::set_error("cuTensorMapEncodeTiled failed for the X digit planes");
+            return SB_ERR_CUDA;
+        }
+        ready = true;
+        return SB_OK;
+    }
+};
+constexpr int SWEEP_COLS = OUTER_BLOCKS * NB;  // columns of the Xk workspace (rows_p x 512)
+
 // W <- W L^{-T} (rows_p x Np, ld rows_p): right-looking block forward substitution, tensor-core
 // products only.  keep: write the result back into W; acc != null: acc[r] += sum_c result[r,c]^2.
-static int32_t trsm_sweep(sb_ctx* c, sb_factor* f, double* W, int64_t rows_p, double* Xk, bool keep, double* acc) {
-    // Xk: rows_p x 256 workspace.  Two block columns per outer step so the big update runs at K = 256.
+// Xk: rows_p x 512 workspace.  With a tcgen05-enabled factor (f->oz) the big update of each outer
+// step (4 block columns, K = 512) runs on the int8 Ozaki kernel; the small in-step products stay DMMA.
+static int32_t trsm_sweep(sb_ctx* c, sb_factor* f, double* W, int64_t rows_p, double* Xk, bool keep, double* acc,
+                          OzSweepWs* ws = nullptr) {
     const int64_t nblk = f->L.nblk(), Np = f->Np;
+    if (f->oz && ws && ws->ready) {
+        for (int64_t k0 = 0; k0 < nblk; k0 += OUTER_BLOCKS) {
+            const int nq = (int)(nblk - k0 < OUTER_BLOCKS ? nblk - k0 : OUTER_BLOCKS);
+            double* X[OUTER_BLOCKS];
+            for (int q = 0; q < nq; q++) {
+                const int64_t kq = k0 + q;
+                double* Wq = W + kq * NB * rows_p;
+                X[q] = Xk + (int64_t)q * NB * rows_p;
+                if (q > 0) {  // bring block column kq up to date with the X panels of this outer step
+                    const double* As[OUTER_BLOCKS]; int64_t las[OUTER_BLOCKS];
+                    const double* Bs[OUTER_BLOCKS]; int64_t lbs[OUTER_BLOCKS];
+                    for (int p = 0; p < q; p++) { As[p] = X[p]; las[p] = rows_p; Bs[p] = f->L.blk(kq, k0 + p); lbs[p] = f->L.ld(k0 + p); }
+                    launch_gemm_nt_seg(q, As, las, Bs, lbs, Wq, rows_p, rows_p, NB, -1.0, 1.0, c->stream);
+                }
+                launch_gemm_nt(Wq, rows_p, f->invL + kq * (int64_t)NB * NB, NB, X[q], rows_p, rows_p, NB, NB, 1.0, 0.0, c->stream);
+                if (keep) SB_CUDA(cudaMemcpyAsync(Wq, X[q], (size_t)rows_p * NB * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                if (acc) launch_rowsumsq_acc(X[q], rows_p, rows_p, NB, acc, c->stream);
+            }
+            const int64_t jt = k0 + nq, m = Np - jt * NB;
+            if (m <= 0) break;
+            OzSrc sx{}, sl{};
+            sx.nseg = sl.nseg = nq;
+            for (int q = 0; q < nq; q++) {
+                sx.base[q] = X[q]; sx.ld[q] = rows_p; sx.rbs[q] = NB;
+                sl.base[q] = f->L.blk(jt, k0 + q); sl.ld[q] = f->L.ld(k0 + q); sl.rbs[q] = NB;
+            }
+            launch_oz_slice(sx, 0, rows_p / NB, 0, ws->rows, ws->scale.d(), reinterpret_cast<int*>(ws->expo.p),
+                            reinterpret_cast<signed char*>(ws->planes.p), c->stream);
+            launch_oz_slice(sl, 0, m / NB, jt * (int64_t)NB, Np, f->oz_scale[0], f->oz_expo[0], f->oz_planes[0], c->stream);
+            if (launch_gemm_ozaki(W + jt * NB * rows_p, rows_p, rows_p, m, nq, &ws->maps, ws->scale.d(), 0, &f->oz_maps[0],
+                                  f->oz_scale[0], jt * (int64_t)NB, &f->oz_desc, f->oz_mode, c->stream) != 0) {
+                sb::set_error("tcgen05 sweep kernel could not be launched");
+                return SB_ERR_CUDA;
+            }
+        }
+        SB_CUDA(cudaGetLastError());
+        return SB_OK;
+    }
+    // DMMA path: two block columns per outer step so the big update runs at K = 256
     double* X0 = Xk;
     double* X1 = Xk + rows_p * NB;
     for (int64_t k0 = 0; k0 < nblk; k0 += 2) {
@@ -1115,11 +1270,13 @@ static int32_t predict_impl(sb_ctx* c, sb_factor* f, const sb_covspec* cross,
         }
     }
     if (need_var) {
-        SB_TRY(Xk.alloc((size_t)Nsp * 2 * NB * sizeof(double)));
+        SB_TRY(Xk.alloc((size_t)Nsp * SWEEP_COLS * sizeof(double)));
         SB_TRY(acc.alloc(Nsp * sizeof(double)));
         SB_CUDA(cudaMemsetAsync(acc.p, 0, Nsp * sizeof(double), c->stream));
         // V^T = W L^{-T}: block forward substitution from the right, tensor-core products only
-        SB_TRY(trsm_sweep(c, f, W.d(), Nsp, Xk.d(), /*keep=*/full_cov, full_cov ? nullptr : acc.d()));
+        OzSweepWs ws(c);
+        if (f->oz) SB_TRY(ws.init(Nsp, f->oz_mode));
+        SB_TRY(trsm_sweep(c, f, W.d(), Nsp, Xk.d(), /*keep=*/full_cov, full_cov ? nullptr : acc.d(), &ws));
         if (!full_cov) {
             SB_TRY(pd.alloc(Nsp * sizeof(double)));
             SB_CUDA(cudaMemsetAsync(pd.p, 0, Nsp * sizeof(double), c->stream));
@@ -1206,6 +1363,57 @@ int32_t sb_predict_factor(sb_ctx* c, sb_factor* f, const sb_covspec* cross, cons
     *out = nullptr;
     if (info) *info = 0;
     return predict_impl(c, f, cross, prior_full, true, nullptr, nullptr, nullptr, noise, out, info);
+}
+
+// ---- gradients of logpdf ------------------------------------------------------------
+// dlogpdf/dtheta = 1/2 tr((alpha alpha' - K^{-1}) dK/dtheta)  -- what Zygote + the ChainRules glue of
+// src/affine_transformations/cross.jl:8-22 deliver in the reference (examples/getting_started/
+// script.jl:154-213).  K^{-1} = L^{-T} L^{-1} is formed once with the tensor-core sweep (I L^{-T}, then
+// one NT product), after which every term costs one fused O(N^2) reduction.
+static __global__ void set_identity_kernel(double* W, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) W[i * n + i] = 1.0;
+}
+static __global__ void qdiag_kernel(const double* alpha, const double* Kinv, int64_t ld, int64_t n, double* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 0.5 * (alpha[i] * alpha[i] - Kinv[i * ld + i]);
+}
+
+int32_t sb_logpdf_grad(sb_ctx* c, sb_factor* f, const sb_covspec* spec, double* g_terms, void* g_noise_diag) {
+    SB_CHECK(c && f && spec && g_terms && g_noise_diag, "null argument");
+    SB_CHECK(f->has_alpha, "sb_logpdf_grad needs alpha: call sb_factor_set_data(delta) first");
+    SB_CHECK(spec->symmetric == 1 && spec->nrows == f->N && spec->ncols == f->N, "spec must be the symmetric N x N spec of the factor");
+    begin_call(c);
+    int64_t before = g_launch_count;
+    const int64_t N = f->N, Np = f->Np;
+    DevSpec ds(c);
+    SB_TRY(ds.build(spec, c->stream, false));
+    DevBuf W(c), Kinv(c), Xk(c), g(c), qd(c);
+    SB_TRY(W.alloc((size_t)Np * Np * sizeof(double)));
+    SB_TRY(Kinv.alloc((size_t)Np * Np * sizeof(double)));
+    SB_TRY(Xk.alloc((size_t)Np * SWEEP_COLS * sizeof(double)));
+    SB_TRY(g.alloc((size_t)2 * (spec->nterms > 0 ? spec->nterms : 1) * sizeof(double)));
+    SB_TRY(qd.alloc((size_t)N * sizeof(double)));
+    SB_CUDA(cudaMemsetAsync(W.p, 0, (size_t)Np * Np * sizeof(double), c->stream));
+    SB_CUDA(cudaMemsetAsync(g.p, 0, (size_t)2 * (spec->nterms > 0 ? spec->nterms : 1) * sizeof(double), c->stream));
+    set_identity_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, c->stream>>>(W.d(), Np);
+    OzSweepWs ws(c);
+    if (f->oz) SB_TRY(ws.init(Np, f->oz_mode));
+    SB_TRY(trsm_sweep(c, f, W.d(), Np, Xk.d(), /*keep=*/true, nullptr, &ws));              // W = L^{-T}
+    launch_gemm_nt(W.d(), Np, W.d(), Np, Kinv.d(), Np, Np, Np, Np, 1.0, 0.0, c->stream);  // K^{-1} = W W'
+    for (auto& b : ds.blocks) {
+        const bool offdiag = b.row0 != b.col0;   // symmetric spec: blocks (i, j), j <= i; (i, i) is the full square
+        launch_grad_reduce(b, f->alpha, Kinv.d(), Np, offdiag ? 2.0 : 1.0, g.d(), c->stream);
+    }
+    qdiag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(f->alpha, Kinv.d(), Np, N, qd.d());
+    g_launch_count += 2;
+    SB_CUDA(cudaGetLastError());
+    if (spec->nterms > 0)
+        SB_CUDA(cudaMemcpyAsync(g_terms, g.p, (size_t)2 * spec->nterms * sizeof(double), cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaMemcpyAsync(g_noise_diag, qd.p, (size_t)N * sizeof(double), cudaMemcpyDefault, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    count_launches(c, before);
+    return SB_OK;
 }
 
 int32_t sb_rand(sb_ctx* c, sb_factor* f, const void* z, int32_t S, void* out) {
@@ -1320,7 +1528,7 @@ int32_t sb_vfe_create(sb_ctx* c, const sb_covspec* uu, const sb_noise* noise_u, 
     VFE_TRY(ddt.alloc(round_up(N, NC) * sizeof(double)));
     VFE_TRY(W.alloc((size_t)NC * Mp * sizeof(double)));
     VFE_TRY(T.alloc((size_t)NC * Mp * sizeof(double)));
-    VFE_TRY(Xk.alloc((size_t)NC * 2 * NB * sizeof(double)));
+    VFE_TRY(Xk.alloc((size_t)NC * SWEEP_COLS * sizeof(double)));
     VFE_TRY(D.alloc((size_t)Mp * Mp * sizeof(double)));
     VFE_TRY(vv.alloc((size_t)(Mp + 8) * sizeof(double)));
     VFE_TRY(fro.alloc((size_t)(nchunks_total + 1) * sizeof(double)));
@@ -1332,6 +1540,8 @@ int32_t sb_vfe_create(sb_ctx* c, const sb_covspec* uu, const sb_noise* noise_u, 
     VFE_CUDA(cudaMemsetAsync(vv.p, 0, (size_t)(Mp + 8) * sizeof(double), c->stream));
     VFE_CUDA(cudaMemsetAsync(fro.p, 0, (size_t)(nchunks_total + 1) * sizeof(double), c->stream));
 
+    OzSweepWs ws(c);
+    if (v->fu->oz) VFE_TRY(ws.init(NC, v->fu->oz_mode));
     for (int64_t ci = c->rank; ci < nchunks_total; ci += c->world) {  // chunks round-robin over ranks
         const int64_t r0 = ci * NC, r1 = r0 + NC < N ? r0 + NC : N;
         const int64_t rows = r1 - r0, rows_p = round_up(rows, NB);
@@ -1341,7 +1551,7 @@ int32_t sb_vfe_create(sb_ctx* c, const sb_covspec* uu, const sb_noise* noise_u, 
         VFE_CUDA(cudaMemsetAsync(W.p, 0, (size_t)rows_p * Mp * sizeof(double), c->stream));
         VFE_TRY(assemble_dense(c, dxu, W.d(), rows_p));
         launch_rowscale(W.d(), rows_p, rows, Mp, dsinv.d() + r0, c->stream);
-        VFE_TRY(trsm_sweep(c, v->fu, W.d(), rows_p, Xk.d(), /*keep=*/true, nullptr));
+        VFE_TRY(trsm_sweep(c, v->fu, W.d(), rows_p, Xk.d(), /*keep=*/true, nullptr, &ws));
         launch_colsumsq(W.d(), rows_p * Mp, 0, 1, fro.d() + ci, c->stream);
         launch_gemv_t(W.d(), rows_p, rows, Mp, ddt.d() + r0, vv.d(), c->stream);
         launch_transpose(W.d(), rows_p, rows_p, Mp, T.d(), Mp, c->stream);
@@ -1416,15 +1626,17 @@ int32_t sb_vfe_predict_cov(sb_ctx* c, sb_vfe* v, const sb_covspec* cross, const 
     SB_TRY(dp.build(prior_full, c->stream, false));
     DevBuf W(c), Xk(c), Cm(c);
     SB_TRY(W.alloc((size_t)Nsp * Mp * sizeof(double)));
-    SB_TRY(Xk.alloc((size_t)Nsp * 2 * NB * sizeof(double)));
+    SB_TRY(Xk.alloc((size_t)Nsp * SWEEP_COLS * sizeof(double)));
     SB_TRY(Cm.alloc((size_t)Nsp * Nsp * sizeof(double)));
     SB_CUDA(cudaMemsetAsync(W.p, 0, (size_t)Nsp * Mp * sizeof(double), c->stream));
     SB_CUDA(cudaMemsetAsync(Cm.p, 0, (size_t)Nsp * Nsp * sizeof(double), c->stream));
     SB_TRY(assemble_dense(c, dc, W.d(), Nsp));
     SB_TRY(assemble_dense(c, dp, Cm.d(), Nsp));
-    SB_TRY(trsm_sweep(c, v->fu, W.d(), Nsp, Xk.d(), true, nullptr));           // W = B'
+    OzSweepWs ws(c);
+    if (v->fu->oz || v->fl->oz) SB_TRY(ws.init(Nsp, v->fu->oz ? v->fu->oz_mode : v->fl->oz_mode));
+    SB_TRY(trsm_sweep(c, v->fu, W.d(), Nsp, Xk.d(), true, nullptr, &ws));      // W = B'
     launch_gemm_nt(W.d(), Nsp, W.d(), Nsp, Cm.d(), Nsp, Nsp, Nsp, Mp, -1.0, 1.0, c->stream);
-    SB_TRY(trsm_sweep(c, v->fl, W.d(), Nsp, Xk.d(), true, nullptr));           // W = (L_Lambda^{-1} B)'
+    SB_TRY(trsm_sweep(c, v->fl, W.d(), Nsp, Xk.d(), true, nullptr, &ws));      // W = (L_Lambda^{-1} B)'
     launch_gemm_nt(W.d(), Nsp, W.d(), Nsp, Cm.d(), Nsp, Nsp, Nsp, Mp, 1.0, 1.0, c->stream);
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaMemcpy2DAsync(cov_out, Ns * sizeof(double), Cm.p, Nsp * sizeof(double), Ns * sizeof(double), Ns,
@@ -1456,7 +1668,7 @@ int32_t sb_vfe_predict(sb_ctx* c, sb_vfe* v, const sb_covspec* cross, const sb_c
     if (var_out) {
         SB_CHECK(prior_diag && prior_diag->nrows == Ns, "prior diag spec required for var");
         SB_TRY(dp.build(prior_diag, c->stream, true));
-        SB_TRY(Xk.alloc((size_t)Nsp * 2 * NB * sizeof(double)));
+        SB_TRY(Xk.alloc((size_t)Nsp * SWEEP_COLS * sizeof(double)));
         SB_TRY(acc1.alloc(Nsp * sizeof(double)));
         SB_TRY(acc2.alloc(Nsp * sizeof(double)));
         SB_TRY(pd.alloc(Nsp * sizeof(double)));
@@ -1464,8 +1676,10 @@ int32_t sb_vfe_predict(sb_ctx* c, sb_vfe* v, const sb_covspec* cross, const sb_c
         SB_CUDA(cudaMemsetAsync(acc2.p, 0, Nsp * sizeof(double), c->stream));
         SB_CUDA(cudaMemsetAsync(pd.p, 0, Nsp * sizeof(double), c->stream));
         // B^T = K_*u L_u^{-T} (kept), then (L_Lambda^{-1} B)^T = B^T L_Lambda^{-T}
-        SB_TRY(trsm_sweep(c, v->fu, W.d(), Nsp, Xk.d(), true, acc1.d()));
-        SB_TRY(trsm_sweep(c, v->fl, W.d(), Nsp, Xk.d(), false, acc2.d()));
+        OzSweepWs ws(c);
+        if (v->fu->oz || v->fl->oz) SB_TRY(ws.init(Nsp, v->fu->oz ? v->fu->oz_mode : v->fl->oz_mode));
+        SB_TRY(trsm_sweep(c, v->fu, W.d(), Nsp, Xk.d(), true, acc1.d(), &ws));
+        SB_TRY(trsm_sweep(c, v->fl, W.d(), Nsp, Xk.d(), false, acc2.d(), &ws));
         SB_TRY(assemble_diag(c, dp, pd.d()));
         launch_sub(pd.d(), pd.d(), acc1.d(), Ns, c->stream);    // k** - |B|^2
         launch_axpy1(pd.d(), acc2.d(), Ns, c->stream);          //     + |L_Lambda^{-1} B|^2

@@ -246,6 +246,73 @@ __global__ void assemble_diag_kernel(BlockDev b, double* __restrict__ out) {
         out[b.row0 + i] = v;
 }
 
+// d kappa / d log(s) for inputs z = s x (stationary kernels; d = |z_i - z_j|): the lengthscale
+// derivative every example optimises (examples/getting_started/script.jl:154-213)
+__device__ __forceinline__ void kappa_and_dlogs(int kernel, double d2, double param, double& k, double& dk) {
+    switch (kernel) {
+        case SB_K_SE: k = exp(-0.5 * d2); dk = -d2 * k; break;
+        case SB_K_MATERN12: { double d = sqrt(d2); k = exp(-d); dk = -d * k; break; }
+        case SB_K_MATERN32: { double s = 1.7320508075688772 * sqrt(d2); double e = exp(-s); k = (1.0 + s) * e; dk = -s * s * e; break; }
+        case SB_K_MATERN52: {
+            double s = 2.23606797749979 * sqrt(d2);
+            double e = exp(-s);
+            k = (1.0 + s + s * s / 3.0) * e;
+            dk = -(s * s / 3.0) * (1.0 + s) * e;
+            break;
+        }
+        case SB_K_CONST: k = param; dk = 0.0; break;
+        default: k = 0.0; dk = 0.0; break;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(const __grid_constant__ BlockDev b, const double* __restrict__ alpha,
+                   const double* __restrict__ Kinv, int64_t ld, double w, double* __restrict__ g) {
+    // tile 64 rows x 32 cols; thread: 1 row x 8 cols
+    const int64_t r = b.row0 + (int64_t)blockIdx.x * 64 + (threadIdx.x & 63);
+    const int64_t c0 = b.col0 + (int64_t)blockIdx.y * 32 + (threadIdx.x >> 6) * 8;
+    double acc[MAX_TERMS][2];
+#pragma unroll
+    for (int t = 0; t < MAX_TERMS; t++) acc[t][0] = acc[t][1] = 0.0;
+    if (r < b.row0 + b.nrows) {
+        const double ar = alpha[r];
+        for (int j = 0; j < 8; j++) {
+            const int64_t c = c0 + j;
+            if (c >= b.col0 + b.ncols) break;
+            const double q = 0.5 * (ar * alpha[c] - Kinv[c * ld + r]);
+            for (int ti = 0; ti < b.nterms; ti++) {
+                const TermDev& t = b.t[ti];
+                const double* x = t.zl + (r - b.row0) * t.dim;
+                const double* y = t.zr + (c - b.col0) * t.dim;
+                double k, dk;
+                if (t.kernel == SB_K_WHITE) { k = all_equal(x, y, t.dim) ? 1.0 : 0.0; dk = 0.0; }
+                else kappa_and_dlogs(t.kernel, sqdist_direct(x, y, t.dim), t.param, k, dk);
+                double sc = q;
+                if (t.sl) sc *= t.sl[r - b.row0];
+                if (t.sr) sc *= t.sr[c - b.col0];
+                acc[ti][0] = fma(sc, k, acc[ti][0]);
+                acc[ti][1] = fma(sc * t.coeff, dk, acc[ti][1]);
+            }
+        }
+    }
+    __shared__ double red[8][MAX_TERMS][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ti = 0; ti < b.nterms; ti++)
+        for (int h = 0; h < 2; h++) {
+            double v = acc[ti][h];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][ti][h] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 2 * b.nterms) {
+        const int ti = threadIdx.x >> 1, h = threadIdx.x & 1;
+        double v = 0.0;
+        for (int wdx = 0; wdx < 8; wdx++) v += red[wdx][ti][h];
+        atomicAdd(&g[2 * b.tix[ti] + h], w * v);
+    }
+}
+
 bool all_1d(const BlockDev& b) {
     for (int t = 0; t < b.nterms; t++)
         if (b.t[t].dim != 1) return false;
@@ -277,6 +344,14 @@ void launch_assemble_packed(const BlockDev& b, Packed out, int64_t N, double sig
         assemble_kernel<true, true><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag, rank, world);
     else
         assemble_kernel<true, false><<<tile_grid(b), 256, 0, s>>>(b, OutDense{nullptr, 0}, out, N, sigma2, noise_diag, rank, world);
+    g_launch_count++;
+}
+
+void launch_grad_reduce(const BlockDev& b, const double* alpha, const double* Kinv, int64_t ld, double w,
+                        double* g, cudaStream_t s) {
+    if (b.nrows == 0 || b.ncols == 0 || b.nterms == 0) return;
+    dim3 grid((unsigned)((b.nrows + 63) / 64), (unsigned)((b.ncols + 31) / 32));
+    grad_reduce_kernel<<<grid, 256, 0, s>>>(b, alpha, Kinv, ld, w, g);
     g_launch_count++;
 }
 

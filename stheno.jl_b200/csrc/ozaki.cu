@@ -31,30 +31,43 @@ namespace {
 
 constexpr int OZ_S = 7;              // digit planes
 constexpr int OZ_BM = 128, OZ_BN = 64;
-constexpr int OZ_KC = 64;            // bytes of K per pipeline stage (two K=32 MMA steps)
-constexpr int OZ_STAGES = 2;
-constexpr int OZ_A_PLANE = OZ_BM * OZ_KC;   // 8192
-constexpr int OZ_B_PLANE = OZ_BN * OZ_KC;   // 4096
-constexpr int OZ_A_STAGE = OZ_S * OZ_A_PLANE;  // 57344
-constexpr int OZ_B_STAGE = OZ_S * OZ_B_PLANE;  // 28672
-constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;  // 86016
 constexpr int OZ_THREADS = 320;
 constexpr int OZ_EPI_WARPS = 8;
-constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int OZ_KMAX = 512;         // bytes of K per row in the digit planes (row pitch)
 
+// Pipeline shape: KC = bytes of K per smem stage, STAGES = ring depth.  The MMA floor is 7.5 us per
+// 128x64x512 tile and a tile needs 688 KB of operands, i.e. ~92 GB/s per SM: with ~1-2 us of TMA
+// latency the ring must keep >= 100-180 KB in flight.  (KC=64, 2 stages) keeps only 84 KB in flight
+// and measured 19.6 us/tile (ncu: tensor pipe 39 %, profiles/ncu_ozaki_r2.txt); (KC=32, 5 stages)
+// keeps 168 KB in flight inside the same shared memory.
+template <int KC, int STAGES>
+struct OzCfg {
+    static constexpr int A_PLANE = OZ_BM * KC;
+    static constexpr int B_PLANE = OZ_BN * KC;
+    static constexpr int A_STAGE = OZ_S * A_PLANE;
+    static constexpr int B_STAGE = OZ_S * B_PLANE;
+    static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+    static constexpr int BAR_BYTES = 16 * STAGES + 16 * OZ_S + 16;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
 struct OzArgs {
+    int mode;         // 1: packed SYRK (A == B == the panel), 0: plain  C[M x Ncols] -= A B^T, dense C
     Packed Pk;
-    int64_t k;        // first block column of the outer step (only for bookkeeping)
-    int64_t J0, w;    // first owned trailing block column, column stride (world)
+    int64_t J0, w;    // packed: first owned trailing block column, column stride (world)
     int64_t total_tiles;
-    int kchunks;      // K / 64
-    const double* scale;  // [Np] row scales s_i = 2^(e_i - 31)
+    int kchunks;      // K / KC
+    const double* scaleA;  // row scales s_i = 2^(e_i - 31), indexed by plane row of A / B
+    const double* scaleB;
+    // plain mode: tile (rt, ct) = (t % mtiles, t / mtiles); plane rows rowA0 + 128 rt, rowB0 + 64 ct
+    double* C;
+    int64_t ldc, mtiles;
+    int64_t rowA0, rowB0;
     // shared-memory matrix descriptor fields (runtime so the test harness can probe encodings)
     uint32_t a_kk_adv, b_kk_adv;  // start-address advance (16-byte units) per K=32 step
     uint32_t a_lbo, b_lbo, sbo;   // 16-byte units
     uint32_t layout;              // 3-bit layout_type (4 = SWIZZLE_64B, 0 = none)
-    int tma_mode;                 // 0: 3-D SWIZZLE_64B box, 1: 4-D un-swizzled interleave
+    int tma_mode;                 // 0: 3-D SWIZZLE_64B box (KC 64), 1: 4-D un-swizzled interleave (KC 64), 2: 3-D SWIZZLE_32B (KC 32)
     int* dbg;                     // optional: raw int32 accumulators of tile 0  [7][128][64]
 };
 
@@ -134,6 +147,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
 
 // same enumeration as gemm_nt.cu's packed-SYRK cursor: owned block columns J0, J0+w, ...; column J
 // holds nblk-J row blocks, two 64-wide half tiles per block
+struct OzTile {
+    int rowA, rowB;    // first plane row of the A (128 rows) / B (64 rows) operand
+    double* C;         // top-left element of the 128 x 64 output tile
+    int64_t ldc;
+};
+
 struct OzCursor {
     int64_t t, J, s0;
     __device__ __forceinline__ void init(const OzArgs& g, int64_t t0) {
@@ -141,6 +160,7 @@ struct OzCursor {
         seek(g);
     }
     __device__ __forceinline__ void seek(const OzArgs& g) {
+        if (g.mode != 1) return;
         const int64_t nblk = g.Pk.nblk();
         while (t < g.total_tiles && t - s0 >= 2 * (nblk - J)) {
             s0 += 2 * (nblk - J);
@@ -151,10 +171,24 @@ struct OzCursor {
         t += step;
         seek(g);
     }
-    __device__ __forceinline__ void tile(const OzArgs& g, int64_t& I, int& h) const {
-        const int64_t loc = t - s0;
-        I = J + (loc >> 1);
-        h = (int)(loc & 1);
+    __device__ __forceinline__ OzTile tile(const OzArgs& g) const {
+        OzTile o;
+        if (g.mode == 1) {
+            const int64_t loc = t - s0;
+            const int64_t I = J + (loc >> 1);
+            const int h = (int)(loc & 1);
+            o.rowA = (int)(I * NB);
+            o.rowB = (int)(J * NB + h * OZ_BN);
+            o.ldc = g.Pk.ld(J);
+            o.C = g.Pk.blk(I, J) + (int64_t)(h * OZ_BN) * o.ldc;
+        } else {
+            const int64_t rt = t % g.mtiles, ct = t / g.mtiles;
+            o.rowA = (int)(g.rowA0 + rt * OZ_BM);
+            o.rowB = (int)(g.rowB0 + ct * OZ_BN);
+            o.ldc = g.ldc;
+            o.C = g.C + ct * OZ_BN * g.ldc + rt * OZ_BM;
+        }
+        return o;
     }
 };
 
@@ -170,18 +204,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return d;
 }
 
+template <int KC, int STAGES>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUtensorMap tmA,
                   const __grid_constant__ CUtensorMap tmB) {
+    using Cfg = OzCfg<KC, STAGES>;
+    constexpr int OZ_STAGES = STAGES, OZ_KC = KC;
+    constexpr int OZ_A_PLANE = Cfg::A_PLANE, OZ_B_PLANE = Cfg::B_PLANE, OZ_A_STAGE = Cfg::A_STAGE;
+    constexpr int OZ_STAGE_BYTES = Cfg::STAGE_BYTES;
     extern __shared__ unsigned char oz_smem_raw[];
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // stage buffers: 1024-byte aligned
     const uint32_t bars = base + OZ_STAGES * OZ_STAGE_BYTES;  // 8-byte mbarriers
-    // layout of the barrier block: full[2], empty[2], tfull[7], tempty[7], tmem ptr
-    const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 32 + 56;
-    const uint32_t tmem_slot = bars + 32 + 112;
+    // layout of the barrier block: full[STAGES], empty[STAGES], tfull[7], tempty[7], tmem ptr
+    const uint32_t full0 = bars, empty0 = bars + 8 * OZ_STAGES, tfull0 = bars + 16 * OZ_STAGES,
+                   tempty0 = tfull0 + 8 * OZ_S;
+    const uint32_t tmem_slot = tempty0 + 8 * OZ_S;
     unsigned char* gen_base = oz_smem_raw + (base - raw);
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + OZ_STAGES * OZ_STAGE_BYTES + 32 + 112);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(gen_base + OZ_STAGES * OZ_STAGE_BYTES + 16 * OZ_STAGES + 16 * OZ_S);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -213,16 +254,15 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
             cur.init(g, blockIdx.x);
             uint32_t n = 0;
             for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x)) {
-                int64_t I; int h;
-                cur.tile(g, I, h);
-                const int rowA = (int)(I * NB), rowB = (int)(cur.J * NB + h * OZ_BN);
+                const OzTile tl = cur.tile(g);
+                const int rowA = tl.rowA, rowB = tl.rowB;
                 for (int kc = 0; kc < g.kchunks; kc++, n++) {
                     const uint32_t st = n % OZ_STAGES, ph = (n / OZ_STAGES) & 1;
                     mbar_wait(empty0 + 8 * st, ph ^ 1);
                     const uint32_t fb = full0 + 8 * st;
                     mbar_expect_tx(fb, OZ_STAGE_BYTES);
                     const uint32_t dA = base + st * OZ_STAGE_BYTES, dB = dA + OZ_A_STAGE;
-                    if (g.tma_mode == 0) {
+                    if (g.tma_mode != 1) {
                         tma_load_3d(dA, &tmA, kc * OZ_KC, rowA, 0, fb);
                         tma_load_3d(dB, &tmB, kc * OZ_KC, rowB, 0, fb);
                     } else {
@@ -278,9 +318,7 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
         cur.init(g, blockIdx.x);
         uint32_t it = 0;
         for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x), it++) {
-            int64_t I; int h;
-            cur.tile(g, I, h);
-            const int64_t J = cur.J;
+            const OzTile tl = cur.tile(g);
             double acc[32];
 #pragma unroll
             for (int c = 0; c < 32; c++) acc[c] = 0.0;
@@ -301,12 +339,12 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
 #pragma unroll
                 for (int c = 0; c < 32; c++) acc[c] = fma((double)v[c], wt, acc[c]);
             }
-            // C[I-block rows, J-block cols h*64 + ch*32 .. +32] -= s_i s_j acc
-            const int64_t ldc = g.Pk.ld(J);
+            // C[rows lq*32 + lane, cols ch*32 .. +32 of the tile] -= s_i s_j acc
+            const int64_t ldc = tl.ldc;
             const int row = lq * 32 + lane;
-            double* cp = g.Pk.blk(I, J) + (int64_t)(h * OZ_BN + ch * 32) * ldc + row;
-            const double si = g.scale[I * NB + row];
-            const double* sj = g.scale + J * NB + h * OZ_BN + ch * 32;
+            double* cp = tl.C + (int64_t)(ch * 32) * ldc + row;
+            const double si = g.scaleA[tl.rowA + row];
+            const double* sj = g.scaleB + tl.rowB + ch * 32;
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 8) {
                 double old[8];
@@ -325,55 +363,53 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
     }
 }
 
-// ---- digit planes of the panels of one outer step ---------------------------------------------
-// The nseg panels live in TILED layout (gemm_nt.cu): element (row block rb, panel column k, row r)
-// at ((rb*128 + k)*132 + r); row block 0 <-> block row k0+1.  Output, for global row i and byte
-// kb = 128*q + k of the outer step's K = 128*nseg:  plane[p][i*512 + kb]  (K-major, 512-byte pitch,
-// exactly the 3-D tensor the TMA box walks), scale[i] = 2^(e_i - 31).
-constexpr int LDT = NB + 4;
-
+// ---- digit planes of an operand panel ------------------------------------------------------------
+// Source: up to 4 segments of 128 columns each (K = 128 * nseg), element (row block rb, column k, row r)
+// of segment q at  base[q] + rb*rbs[q] + k*ld[q] + r  -- covers both the TILED Cholesky panels of
+// gemm_nt.cu (rbs = 128*132, ld = 132) and plain column-major panels (rbs = 128, ld = ld).
+// Output, for plane row i = out_row_base + rb*128 + r and byte kb = 128*q + k:
+//   plane[p][i*512 + kb]  (K-major, 512-byte pitch: the 3-D tensor the TMA box walks),
+//   scale[i] = 2^(e_i - 31),  expo[i] = e_i.
 __global__ void __launch_bounds__(512)
-oz_rowscale_kernel(const double* const* __restrict__ Pt4, int nseg, int64_t k0, int64_t rb_lo,
-                   double* __restrict__ scale, int* __restrict__ expo) {
+oz_rowscale_kernel(const OzSrc src, int64_t rb_lo, int64_t out_row_base, double* __restrict__ scale,
+                   int* __restrict__ expo) {
     // one CTA per 128-row block; 512 threads = 128 rows x 4 column groups
     __shared__ double red[4][NB];
     const int64_t rb = rb_lo + blockIdx.x;
     const int r = threadIdx.x & 127, cg = threadIdx.x >> 7;
     double m = 0.0;
-    for (int q = 0; q < nseg; q++) {
-        const double* P = Pt4[q] + (rb * NB) * (int64_t)LDT + r;
-        for (int k = cg; k < NB; k += 4) m = fmax(m, fabs(P[(int64_t)k * LDT]));
+    for (int q = 0; q < src.nseg; q++) {
+        const double* P = src.base[q] + rb * src.rbs[q] + r;
+        const int64_t ld = src.ld[q];
+        for (int k = cg; k < NB; k += 4) m = fmax(m, fabs(P[(int64_t)k * ld]));
     }
     red[cg][r] = m;
     __syncthreads();
     if (cg == 0) {
         m = fmax(fmax(red[0][r], red[1][r]), fmax(red[2][r], red[3][r]));
-        const int64_t i = (k0 + 1 + rb) * NB + r;
-        int e = 0;
-        double s = 0.0;
-        if (m > 1e-280 && m < 1e280) {
-            e = ilogb(m) + 2;               // |x| * 2^-e < 0.5
-            s = scalbn(1.0, e - 31);
-        }
-        scale[i] = s;
-        expo[i] = (m > 1e-280 && m < 1e280) ? e : 0x7fffffff;
+        const int64_t i = out_row_base + rb * NB + r;
+        const bool ok = m > 1e-280 && m < 1e280;
+        const int e = ok ? ilogb(m) + 2 : 0;   // |x| * 2^-e < 0.5
+        scale[i] = ok ? scalbn(1.0, e - 31) : 0.0;
+        expo[i] = ok ? e : 0x7fffffff;
     }
 }
 
 __global__ void __launch_bounds__(256)
-oz_slice_kernel(const double* const* __restrict__ Pt4, int nseg, int64_t k0, int64_t rb_lo, int64_t Np,
+oz_slice_kernel(const OzSrc src, int64_t rb_lo, int64_t out_row_base, int64_t plane_rows,
                 const int* __restrict__ expo, signed char* __restrict__ planes) {
     // grid: (row blocks, nseg * 4 column chunks of 32); 256 threads = 128 rows x 2 halves of 16 cols
     __shared__ __align__(16) signed char sd[OZ_S][NB][32];
     const int64_t rb = rb_lo + blockIdx.x;
     const int q = blockIdx.y >> 2, kc = blockIdx.y & 3;
     const int r = threadIdx.x & 127, kh = threadIdx.x >> 7;
-    const int64_t i = (k0 + 1 + rb) * NB + r;
-    const int e = expo[i];
-    const double* P = Pt4[q] + (rb * NB + kc * 32 + kh * 16) * (int64_t)LDT + r;
+    const int64_t row0 = out_row_base + rb * NB;
+    const int e = expo[row0 + r];
+    const int64_t ld = src.ld[q];
+    const double* P = src.base[q] + rb * src.rbs[q] + (int64_t)(kc * 32 + kh * 16) * ld + r;
 #pragma unroll 4
     for (int kk = 0; kk < 16; kk++) {
-        const double x = P[(int64_t)kk * LDT];
+        const double x = P[(int64_t)kk * ld];
         long long Z = 0x0000808080808080LL;
         if (e != 0x7fffffff) Z += __double2ll_rn(scalbn(x, 55 - e));
         const int kb = kh * 16 + kk;
@@ -383,11 +419,10 @@ oz_slice_kernel(const double* const* __restrict__ Pt4, int nseg, int64_t k0, int
     }
     __syncthreads();
     // 7 planes x 128 rows x 32 bytes: 16-byte stores, two per row
-    const int64_t row0 = (k0 + 1 + rb) * NB;
     for (int idx = threadIdx.x; idx < OZ_S * NB * 2; idx += 256) {
         const int p = idx / (NB * 2), rr = (idx >> 1) & 127, hf = idx & 1;
         const int4 v = *reinterpret_cast<const int4*>(&sd[p][rr][hf * 16]);
-        *reinterpret_cast<int4*>(planes + ((int64_t)p * Np + row0 + rr) * OZ_KMAX + q * NB + kc * 32 + hf * 16) = v;
+        *reinterpret_cast<int4*>(planes + ((int64_t)p * plane_rows + row0 + rr) * OZ_KMAX + q * NB + kc * 32 + hf * 16) = v;
     }
 }
 
@@ -398,6 +433,12 @@ EncodeTiled_t g_encode = nullptr;
 bool g_oz_attr = false;
 int g_oz_sms = 0;
 
+// tma_mode -> (KC, STAGES) instance
+#define OZ_DISPATCH(mode, CALL)                                  \
+    do {                                                         \
+        if ((mode) == 2) { CALL(32, 5); } else { CALL(64, 2); }  \
+    } while (0)
+
 int oz_init() {
     if (!g_encode) {
         void* fn = nullptr;
@@ -406,7 +447,10 @@ int oz_init() {
         g_encode = (EncodeTiled_t)fn;
     }
     if (!g_oz_attr) {
-        if (cudaFuncSetAttribute(ozaki_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(ozaki_syrk_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)OzCfg<64, 2>::SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(ozaki_syrk_kernel<32, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)OzCfg<32, 5>::SMEM) != cudaSuccess) return -2;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_oz_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -426,23 +470,25 @@ int oz_make_maps(signed char* planes, int64_t Np, int tma_mode, OzMaps* out) {
     CUtensorMap* ma = reinterpret_cast<CUtensorMap*>(out->a);
     CUtensorMap* mb = reinterpret_cast<CUtensorMap*>(out->b);
     CUresult r1, r2;
-    if (tma_mode == 0) {
+    if (tma_mode == 0 || tma_mode == 2) {
+        const cuuint32_t kc = tma_mode == 0 ? 64 : 32;
+        const CUtensorMapSwizzle sw = tma_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
         cuuint64_t dims[3] = {(cuuint64_t)OZ_KMAX, (cuuint64_t)Np, (cuuint64_t)OZ_S};
         cuuint64_t strides[2] = {(cuuint64_t)OZ_KMAX, (cuuint64_t)Np * OZ_KMAX};
         cuuint32_t estr[3] = {1, 1, 1};
-        cuuint32_t boxA[3] = {OZ_KC, OZ_BM, OZ_S}, boxB[3] = {OZ_KC, OZ_BN, OZ_S};
+        cuuint32_t boxA[3] = {kc, OZ_BM, OZ_S}, boxB[3] = {kc, OZ_BN, OZ_S};
         r1 = g_encode(ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes, dims, strides, boxA, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         r2 = g_encode(mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes, dims, strides, boxB, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         // un-swizzled "interleave" operand layout: smem [plane][16-byte k column][row][16 B]
         cuuint64_t dims[4] = {16, (cuuint64_t)Np, (cuuint64_t)(OZ_KMAX / 16), (cuuint64_t)OZ_S};
         cuuint64_t strides[3] = {(cuuint64_t)OZ_KMAX, 16, (cuuint64_t)Np * OZ_KMAX};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        cuuint32_t boxA[4] = {16, OZ_BM, OZ_KC / 16, OZ_S}, boxB[4] = {16, OZ_BN, OZ_KC / 16, OZ_S};
+        cuuint32_t boxA[4] = {16, OZ_BM, 64 / 16, OZ_S}, boxB[4] = {16, OZ_BN, 64 / 16, OZ_S};
         r1 = g_encode(ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, planes, dims, strides, boxA, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -453,17 +499,22 @@ int oz_make_maps(signed char* planes, int64_t Np, int tma_mode, OzMaps* out) {
     return (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) ? 0 : -3;
 }
 
-// digit planes + row scales of the rows [jt*128, Np) from the nseg tiled panels of the outer step
-// starting at block column k0 (Pt_dev: device array of the nseg tiled-panel base pointers)
-void launch_oz_slice(const double* const* Pt_dev, int nseg, int64_t k0, int64_t Np, double* scale, int* expo,
-                     signed char* planes, cudaStream_t s) {
-    const int64_t nblk = Np / NB;
-    const int64_t rb_lo = nseg - 1;                     // first trailing row block (block row k0 + nseg)
-    const int64_t nrb = nblk - (k0 + nseg);
-    if (nrb <= 0) return;
-    oz_rowscale_kernel<<<(unsigned)nrb, 512, 0, s>>>(Pt_dev, nseg, k0, rb_lo, scale, expo);
-    oz_slice_kernel<<<dim3((unsigned)nrb, (unsigned)(nseg * 4)), 256, 0, s>>>(Pt_dev, nseg, k0, rb_lo, Np, expo, planes);
+// digit planes + row scales of row blocks [rb_lo, rb_lo + nrb) of the source panel
+void launch_oz_slice(const OzSrc& src, int64_t rb_lo, int64_t nrb, int64_t out_row_base, int64_t plane_rows,
+                     double* scale, int* expo, signed char* planes, cudaStream_t s) {
+    if (nrb <= 0 || src.nseg <= 0) return;
+    oz_rowscale_kernel<<<(unsigned)nrb, 512, 0, s>>>(src, rb_lo, out_row_base, scale, expo);
+    oz_slice_kernel<<<dim3((unsigned)nrb, (unsigned)(src.nseg * 4)), 256, 0, s>>>(src, rb_lo, out_row_base, plane_rows,
+                                                                                  expo, planes);
     g_launch_count += 2;
+}
+
+// the nseg TILED panels of the Cholesky outer step at block column k0 (row block 0 <-> block row k0+1)
+OzSrc oz_src_tiled(const double* const* Pt, int nseg) {
+    OzSrc src{};
+    src.nseg = nseg;
+    for (int q = 0; q < nseg; q++) { src.base[q] = Pt[q]; src.ld[q] = NB + 4; src.rbs[q] = (int64_t)NB * (NB + 4); }
+    return src;
 }
 
 void oz_default_desc(OzDesc* d, int tma_mode) {
@@ -472,6 +523,11 @@ void oz_default_desc(OzDesc* d, int tma_mode) {
         d->a_lbo = d->b_lbo = 1;        // unused for swizzled K-major
         d->sbo = 32;                    // 8 rows x 64 B
         d->layout = 4;                  // SWIZZLE_64B
+    } else if (tma_mode == 2) {
+        d->a_kk_adv = d->b_kk_adv = 0;  // one K=32 step per stage
+        d->a_lbo = d->b_lbo = 1;
+        d->sbo = 16;                    // 8 rows x 32 B
+        d->layout = 6;                  // SWIZZLE_32B
     } else {
         d->a_kk_adv = 2 * (OZ_BM * 16 >> 4);  // two 16-byte k columns of 128 rows
         d->b_kk_adv = 2 * (OZ_BN * 16 >> 4);
@@ -480,6 +536,26 @@ void oz_default_desc(OzDesc* d, int tma_mode) {
         d->sbo = 8;                           // next 8-row core matrix: 128 B
         d->layout = 0;
     }
+}
+
+static void oz_fill_desc(OzArgs& g, const OzDesc* desc, int tma_mode, int* dbg) {
+    g.a_kk_adv = desc->a_kk_adv; g.b_kk_adv = desc->b_kk_adv;
+    g.a_lbo = desc->a_lbo; g.b_lbo = desc->b_lbo; g.sbo = desc->sbo; g.layout = desc->layout;
+    g.tma_mode = tma_mode;
+    g.dbg = dbg;
+}
+
+static int oz_launch(OzArgs& g, const OzMaps* mapsA, const OzMaps* mapsB, cudaStream_t s, int reserve_sms) {
+    int64_t cap = g_oz_sms - reserve_sms;
+    if (cap < 1) cap = 1;
+    const int64_t grid = g.total_tiles < cap ? g.total_tiles : cap;
+    const CUtensorMap* ma = reinterpret_cast<const CUtensorMap*>(mapsA->a);
+    const CUtensorMap* mb = reinterpret_cast<const CUtensorMap*>(mapsB->b);
+#define OZ_LAUNCH(KC, ST) ozaki_syrk_kernel<KC, ST><<<(unsigned)grid, OZ_THREADS, OzCfg<KC, ST>::SMEM, s>>>(g, *ma, *mb)
+    OZ_DISPATCH(g.tma_mode, OZ_LAUNCH);
+#undef OZ_LAUNCH
+    g_launch_count++;
+    return 0;
 }
 
 // A[I, J] -= P_I P_J^T on the packed lower matrix for the owned block columns J in [jlo, jhi), with
@@ -495,22 +571,32 @@ int launch_syrk_ozaki(Packed Apk, int64_t k, int nseg, int64_t jlo, int64_t jhi,
     const int64_t tiles = syrk_packed_tiles(nblk, k, jlo, jhi, rank, world);
     if (tiles <= 0 || nseg <= 0) return 0;
     OzArgs g{};
-    g.Pk = Apk; g.k = k; g.J0 = J0; g.w = world;
+    g.mode = 1;
+    g.Pk = Apk; g.J0 = J0; g.w = world;
     g.total_tiles = tiles * 2;
-    g.kchunks = nseg * NB / OZ_KC;
-    g.scale = scale;
-    g.a_kk_adv = desc->a_kk_adv; g.b_kk_adv = desc->b_kk_adv;
-    g.a_lbo = desc->a_lbo; g.b_lbo = desc->b_lbo; g.sbo = desc->sbo; g.layout = desc->layout;
-    g.tma_mode = tma_mode;
-    g.dbg = dbg;
-    int64_t cap = g_oz_sms - reserve_sms;
-    if (cap < 1) cap = 1;
-    const int64_t grid = g.total_tiles < cap ? g.total_tiles : cap;
-    const CUtensorMap* ma = reinterpret_cast<const CUtensorMap*>(maps->a);
-    const CUtensorMap* mb = reinterpret_cast<const CUtensorMap*>(maps->b);
-    ozaki_syrk_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, s>>>(g, *ma, *mb);
-    g_launch_count++;
-    return 0;
+    g.kchunks = nseg * NB / (tma_mode == 2 ? 32 : 64);
+    g.scaleA = g.scaleB = scale;
+    oz_fill_desc(g, desc, tma_mode, dbg);
+    return oz_launch(g, maps, maps, s, reserve_sms);
+}
+
+// plain product  C[M x Ncols] -= A B^T  (C dense column-major, ldc; M % 128 == 0, Ncols % 64 == 0):
+// A = plane rows [rowA0, rowA0 + M) of the (mapsA, scaleA) set, B = plane rows [rowB0, rowB0 + Ncols) of
+// (mapsB, scaleB); K = 128 * nseg.  Used by the posterior / VFE matrix-TRSM sweeps.
+int launch_gemm_ozaki(double* C, int64_t ldc, int64_t M, int64_t Ncols, int nseg, const OzMaps* mapsA,
+                      const double* scaleA, int64_t rowA0, const OzMaps* mapsB, const double* scaleB, int64_t rowB0,
+                      const OzDesc* desc, int tma_mode, cudaStream_t s) {
+    if (oz_init() != 0) return -1;
+    if (M <= 0 || Ncols <= 0 || nseg <= 0) return 0;
+    OzArgs g{};
+    g.mode = 0;
+    g.C = C; g.ldc = ldc; g.mtiles = M / OZ_BM;
+    g.total_tiles = (M / OZ_BM) * (Ncols / OZ_BN);
+    g.kchunks = nseg * NB / (tma_mode == 2 ? 32 : 64);
+    g.scaleA = scaleA; g.scaleB = scaleB;
+    g.rowA0 = rowA0; g.rowB0 = rowB0;
+    oz_fill_desc(g, desc, tma_mode, nullptr);
+    return oz_launch(g, mapsA, mapsB, s, 0);
 }
 
 }  // namespace sb

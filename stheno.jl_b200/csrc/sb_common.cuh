@@ -82,6 +82,7 @@ struct BlockDev {
     int32_t nterms;
     int32_t accumulate;  // 1: add to existing output (blocks with > MAX_TERMS terms)
     TermDev t[MAX_TERMS];
+    int32_t tix[MAX_TERMS];  // index of each term in the caller's sb_covspec (gradient output slot)
 };
 
 // output target of the assembly kernel
@@ -97,6 +98,13 @@ void launch_assemble_packed(const BlockDev& b, Packed out, int64_t N, double sig
                             const double* noise_diag, cudaStream_t s, int rank = 0, int world = 1);
 void launch_fill_padding(Packed out, int64_t N, cudaStream_t s);
 void launch_assemble_diag(const BlockDev& b, double* out, cudaStream_t s);
+// gradient reduction (sb_logpdf_grad): for every term t of block b
+//   g[2*tix]   += w * sum_ij Q_ij sl_i sr_j kappa_t(i,j)              (d/d coeff_t)
+//   g[2*tix+1] += w * sum_ij Q_ij coeff sl_i sr_j dkappa_t/dlog(s)    (d/d log input-scale)
+// with Q_ij = (alpha_i alpha_j - Kinv_ij)/2, Kinv dense column-major (ld); w = 2 for strictly
+// off-diagonal blocks of a symmetric spec.
+void launch_grad_reduce(const BlockDev& b, const double* alpha, const double* Kinv, int64_t ld, double w,
+                        double* g, cudaStream_t s);
 
 // potrf of diagonal block k (in place in the packed matrix) + explicit inverse of L_kk
 // (dense NB x NB, ld NB) + per-block sum of log pivots + first failing pivot (1-based, 0 = ok)
@@ -136,6 +144,9 @@ void launch_trsv_diag(const double* invL, double* b, int64_t Np, int S, bool tra
                       cudaStream_t s);
 void launch_gemv_below(Packed L, int64_t k, double* b, int S, cudaStream_t s);
 void launch_gemvT_below(Packed L, int64_t k, double* b, int S, cudaStream_t s);
+// one-launch persistent sweep (solve.cu): flags = 2*nblk unsigned scratch
+void launch_sweep(Packed L, const double* invL, double* b, int S, bool backward, unsigned* flags, int num_sms,
+                  cudaStream_t s);
 void launch_colsumsq(const double* v, int64_t n, int64_t ld, int S, double* out, cudaStream_t s);
 // y[M] (+)= W[M x n] * a[n]   (W column-major, ld)
 void launch_gemv_n(const double* W, int64_t ld, int64_t M, int64_t n, const double* a, double* y,
@@ -166,12 +177,20 @@ struct OzDesc { uint32_t a_kk_adv, b_kk_adv, a_lbo, b_lbo, sbo, layout; };
 size_t oz_planes_bytes(int64_t Np);                       // 7 digit planes, 512-byte row pitch
 int oz_make_maps(signed char* planes, int64_t Np, int tma_mode, OzMaps* out);
 void oz_default_desc(OzDesc* d, int tma_mode);
-// Pt_dev: DEVICE array of the nseg tiled-panel base pointers of the outer step at block column k0
-void launch_oz_slice(const double* const* Pt_dev, int nseg, int64_t k0, int64_t Np, double* scale, int* expo,
-                     signed char* planes, cudaStream_t s);
+// source panel of the slicer: up to 4 segments of 128 columns; element (row block rb, col k, row r) of
+// segment q at base[q] + rb*rbs[q] + k*ld[q] + r
+struct OzSrc { const double* base[4]; int64_t ld[4]; int64_t rbs[4]; int nseg; };
+OzSrc oz_src_tiled(const double* const* Pt, int nseg);
+void launch_oz_slice(const OzSrc& src, int64_t rb_lo, int64_t nrb, int64_t out_row_base, int64_t plane_rows,
+                     double* scale, int* expo, signed char* planes, cudaStream_t s);
 int launch_syrk_ozaki(Packed A, int64_t k, int nseg, int64_t jlo, int64_t jhi, int rank, int world,
                       const OzMaps* maps, const double* scale, const OzDesc* desc, int tma_mode, cudaStream_t s,
                       int reserve_sms = 0, int* dbg = nullptr);
+
+// plain product C[M x Ncols] -= A B^T through the same kernel (dense column-major C)
+int launch_gemm_ozaki(double* C, int64_t ldc, int64_t M, int64_t Ncols, int nseg, const OzMaps* mapsA,
+                      const double* scaleA, int64_t rowA0, const OzMaps* mapsB, const double* scaleB, int64_t rowB0,
+                      const OzDesc* desc, int tma_mode, cudaStream_t s);
 
 extern thread_local int64_t g_launch_count;
 

@@ -104,6 +104,192 @@ gemvT_below_kernel(Packed L, int64_t k, double* __restrict__ b, int S) {
     }
 }
 
+// ---- persistent triangular sweep ------------------------------------------------------------
+// One launch per sweep instead of 2 launches per 128-wide block (1024 tiny dependent launches at
+// N = 65536, 0.2 of the HBM roofline in round 1).  Right-looking data flow with static ownership:
+//   forward  b <- L^{-1} b :  when x_k = invL_kk b_k is final, every block row i > k applies
+//                             b_i -= L[i,k] x_k;  b_{k+1} is final after k+1 such updates.
+//   backward b <- L^{-T} b :  when x_k = invL_kk^T b_k is final, every block j < k applies
+//                             b_j -= L[k,j]^T x_k.
+// Block i (resp. j) is owned by worker CTA (i mod W) for the whole sweep, so updates of one block
+// are sequential inside one CTA: no atomics on b, bit-reproducible results.  The last CTA only does
+// the diagonal solves; cross-CTA ordering goes through per-block flags (ready[k]: x_k final,
+// done[k]: number of updates applied to b_k) with release/acquire fences; b is read with ld.cg
+// where another SM wrote it.  Each element of L is read exactly once (HBM-bound, 17.2 GB/sweep).
+struct SweepArgs {
+    Packed L;
+    const double* invL;
+    double* b;        // Np x S, leading dimension L.Np
+    int S;
+    unsigned* ready;  // [nblk]
+    unsigned* done;   // [nblk]
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const unsigned* p, unsigned target) {
+    long long t0 = 0;
+    for (unsigned it = 0; ld_acquire(p) < target; it++) {
+        if ((it & 0x3ff) == 0x3ff) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 40000000000LL) __trap();  // ~20 s: protocol bug, never hang the box
+        }
+    }
+}
+
+// out[r] (+)= sign * sum_c M[r, c] x[c]  for a 128 x 128 column-major block (ld), x in shared memory.
+// 256 threads: thread (r, h) sums 64 columns; halves are combined through shared memory.
+template <bool OVERWRITE>
+__device__ __forceinline__ void block_matvec_n(const double* __restrict__ M, int64_t ld, const double (*xs)[NB],
+                                               double* __restrict__ out, int64_t ldo, int S, double (*red)[NB]) {
+    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+    const double* p = M + r + (int64_t)(h * 64) * ld;
+    double acc[MAXS];
+#pragma unroll
+    for (int s = 0; s < MAXS; s++) acc[s] = 0.0;
+#pragma unroll 16
+    for (int c = 0; c < 64; c++) {
+        const double l = __ldcs(p + (int64_t)c * ld);
+#pragma unroll
+        for (int s = 0; s < MAXS; s++)
+            if (s < S) acc[s] = fma(l, xs[s][h * 64 + c], acc[s]);
+    }
+    if (h == 1) {
+#pragma unroll
+        for (int s = 0; s < MAXS; s++)
+            if (s < S) red[s][r] = acc[s];
+    }
+    __syncthreads();
+    if (h == 0) {
+#pragma unroll
+        for (int s = 0; s < MAXS; s++)
+            if (s < S) {
+                const double t = acc[s] + red[s][r];
+                if (OVERWRITE) out[(int64_t)s * ldo + r] = t;
+                else out[(int64_t)s * ldo + r] -= t;
+            }
+    }
+    __syncthreads();
+}
+
+// out[c] (+)= sign * sum_r M[r, c] x[r]  (transposed product); warp w owns columns 16w .. 16w+15
+template <bool OVERWRITE>
+__device__ __forceinline__ void block_matvec_t(const double* __restrict__ M, int64_t ld, const double (*xs)[NB],
+                                               double* __restrict__ out, int64_t ldo, int S) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int s = 0; s < S; s++) {
+        double xr[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) xr[i] = xs[s][lane + 32 * i];
+        double part[16];
+#pragma unroll
+        for (int cc = 0; cc < 16; cc++) {
+            const double* colp = M + (int64_t)(warp * 16 + cc) * ld + lane;
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) a = fma(__ldcs(colp + 32 * i), xr[i], a);
+            part[cc] = a;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 16; cc++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part[cc] += __shfl_xor_sync(0xffffffffu, part[cc], o);
+        }
+        if (lane < 16) {
+            double v = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 16; cc++) v = (lane == cc) ? part[cc] : v;
+            double* o = out + (int64_t)s * ldo + warp * 16 + lane;
+            if (OVERWRITE) *o = v; else *o -= v;
+        }
+    }
+    __syncthreads();
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256) sweep_kernel(SweepArgs a) {
+    __shared__ double xs[MAXS][NB];
+    __shared__ double red[MAXS][NB];
+    const int64_t nblk = a.L.nblk(), Np = a.L.Np;
+    const int S = a.S;
+    const int G = gridDim.x;
+    const int W = G > 1 ? G - 1 : 1;              // worker CTAs; CTA G-1 does the diagonal solves
+    auto load_x = [&](int64_t k) {                 // x_k (written by another SM) -> shared memory
+        for (int idx = threadIdx.x; idx < S * NB; idx += 256) {
+            const int s = idx / NB, c = idx % NB;
+            xs[s][c] = __ldcg(a.b + (int64_t)s * Np + k * NB + c);
+        }
+        __syncthreads();
+    };
+    auto diag_solve = [&](int64_t k) {
+        load_x(k);
+        const double* Mk = a.invL + k * (int64_t)NB * NB;
+        if (!BACKWARD) block_matvec_n<true>(Mk, NB, xs, a.b + k * NB, Np, S, red);
+        else block_matvec_t<true>(Mk, NB, xs, a.b + k * NB, Np, S);
+    };
+    auto update = [&](int64_t tgt, int64_t k) {   // block `tgt` absorbs x_k (already in xs)
+        if (!BACKWARD) block_matvec_n<false>(a.L.blk(tgt, k), a.L.ld(k), xs, a.b + tgt * NB, Np, S, red);
+        else block_matvec_t<false>(a.L.blk(k, tgt), a.L.ld(tgt), xs, a.b + tgt * NB, Np, S);
+    };
+
+    if (G == 1) {  // tiny problems: one CTA does everything in order
+        for (int64_t kk = 0; kk < nblk; kk++) {
+            const int64_t k = BACKWARD ? nblk - 1 - kk : kk;
+            diag_solve(k);
+            __syncthreads();
+            load_x(k);
+            if (!BACKWARD) { for (int64_t i = k + 1; i < nblk; i++) update(i, k); }
+            else           { for (int64_t j = k - 1; j >= 0; j--) update(j, k); }
+        }
+        return;
+    }
+
+    if ((int)blockIdx.x == G - 1) {
+        // ---- diagonal solves, in dependency order ----
+        for (int64_t kk = 0; kk < nblk; kk++) {
+            const int64_t k = BACKWARD ? nblk - 1 - kk : kk;
+            if (threadIdx.x == 0) spin_until(a.done + k, (unsigned)kk);  // all kk updates of b_k applied
+            __syncthreads();
+            diag_solve(k);
+            if (threadIdx.x == 0) { __threadfence(); st_release(a.ready + k, 1u); }
+        }
+        return;
+    }
+    // ---- workers ----
+    const int me = blockIdx.x;
+    for (int64_t kk = 0; kk + 1 < nblk; kk++) {
+        const int64_t k = BACKWARD ? nblk - 1 - kk : kk;
+        // nearest owned target first (it gates the next diagonal solve); skip steps with no work
+        int64_t first;
+        if (!BACKWARD) { first = k + 1 + (((me - (k + 1)) % W) + W) % W; if (first >= nblk) continue; }
+        else           { first = k - 1 - ((((k - 1) - me) % W) + W) % W; if (first < 0) continue; }
+        if (threadIdx.x == 0) spin_until(a.ready + k, 1u);
+        __syncthreads();
+        load_x(k);
+        if (!BACKWARD) {
+            for (int64_t i = first; i < nblk; i += W) {
+                update(i, k);
+                if (threadIdx.x == 0) { __threadfence(); red_release_add(a.done + i, 1u); }
+            }
+        } else {
+            for (int64_t j = first; j >= 0; j -= W) {
+                update(j, k);
+                if (threadIdx.x == 0) { __threadfence(); red_release_add(a.done + j, 1u); }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 colsumsq_kernel(const double* __restrict__ v, int64_t n, int64_t ld, double* __restrict__ out) {
     const double* p = v + (int64_t)blockIdx.y * ld;
@@ -266,6 +452,20 @@ __global__ void add_diag_kernel(Packed L, const double* __restrict__ d, int64_t 
 }
 
 }  // namespace
+
+
+// whole forward (backward = true: transposed) sweep b <- L^{-1} b / L^{-T} b in ONE launch;
+// flags: 2*nblk unsigned scratch (zeroed here)
+void launch_sweep(Packed L, const double* invL, double* b, int S, bool backward, unsigned* flags, int num_sms,
+                  cudaStream_t s) {
+    const int64_t nblk = L.nblk();
+    cudaMemsetAsync(flags, 0, 2 * nblk * sizeof(unsigned), s);
+    SweepArgs a{L, invL, b, S, flags, flags + nblk};
+    int grid = nblk < 4 ? 1 : (int)(nblk + 1 < num_sms ? nblk + 1 : num_sms);
+    if (backward) sweep_kernel<true><<<grid, 256, 0, s>>>(a);
+    else sweep_kernel<false><<<grid, 256, 0, s>>>(a);
+    g_launch_count++;
+}
 
 void launch_add_dense_lower(Packed L, const double* D, int64_t ld, int64_t n, cudaStream_t st) {
     if (n <= 0) return;

@@ -46,6 +46,23 @@ class _Factor:
         _lib.check(_lib.load().sb_factor_logdet(self.ctx.h, self.h, C.byref(v)))
         return v.value
 
+    def export(self) -> np.ndarray:
+        """Checkpoint: header | packed L | diagonal-block inverses | alpha as one uint8 array."""
+        n = C.c_int64(0)
+        lib = _lib.load()
+        _lib.check(lib.sb_factor_export_size(self.ctx.h, self.h, C.byref(n)))
+        blob = np.empty(n.value, dtype=np.uint8)
+        _lib.check(lib.sb_factor_export(self.ctx.h, self.h, blob.ctypes.data, n.value))
+        return blob
+
+    @staticmethod
+    def load(blob: np.ndarray, n: int, ctx=None) -> "_Factor":
+        ctx = ctx or _ctx()
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        _lib.check(_lib.load().sb_factor_import(ctx.h, blob.ctypes.data, blob.size, C.byref(h)))
+        return _Factor(h, ctx, n)
+
     def to_dense_L(self):
         L = np.empty((self.n, self.n), dtype=np.float64, order="F")
         _lib.check(_lib.load().sb_factor_get_L(self.ctx.h, self.h, L.ctypes.data))
@@ -138,6 +155,64 @@ class FiniteGP:
             _lib.check(st, info)
             self._factor = _Factor(h, ctx, lx.n)
         return self._factor
+
+
+class LogpdfGradient:
+    """Gradient of logpdf(fx, y) w.r.t. the parameters the lowered plan exposes.
+
+    noise:    d/d sigma^2 (scalar noise) or d/d diag(Sigma_y) (vector noise).
+    kernels:  list of dicts, one per (atomic leaf, kernel component): `atom`, `component` (index into
+              the leaf kernel's lowered sum), `kernel_id`, `coeff` / `input_scale` (current values),
+              `dcoeff` = d/d(component multiplier, i.e. the kernel variance),
+              `dlogscale` = d/d log(input scale)  (= -d/d log(lengthscale)).
+    The caller applies its own chain rule, exactly as Zygote does through user code in the reference."""
+
+    def __init__(self, noise, kernels):
+        self.noise, self.kernels = noise, kernels
+
+    def for_atom(self, atom, component=0):
+        for k in self.kernels:
+            if k["atom"] is atom and k["component"] == component:
+                return k
+        raise KeyError("no such leaf / component in this gradient")
+
+
+def grad_logpdf(fx: "FiniteGP", y) -> LogpdfGradient:
+    """d logpdf(fx, y) / d theta = 1/2 tr((alpha alpha' - K^-1) dK/dtheta) on the device."""
+    if fx.post is not None or isinstance(fx, SparseFiniteGP):
+        raise NotImplementedError("grad_logpdf: prior FiniteGPs only")
+    if np.ndim(fx.noise) == 2:
+        raise NotImplementedError("grad_logpdf: scalar or diagonal observation noise")
+    post = posterior(fx, y)
+    post._install_alpha()
+    lx = fx.lowered
+    spec = spec_symmetric(lx)
+    g = np.zeros(2 * max(1, spec.nterms), dtype=np.float64)
+    qd = np.empty(lx.n, dtype=np.float64)
+    fac = post.fac
+    _lib.check(_lib.load().sb_logpdf_grad(fac.ctx.h, fac.h, C.byref(spec), g.ctypes.data, qd.ctypes.data))
+    agg = {}
+    for t, (atom, key, ci, kid, pair_coeff, kc, iscale) in enumerate(spec._meta):
+        e = agg.setdefault((id(atom), key, ci), dict(atom=atom, component=ci, kernel_id=kid, coeff=kc,
+                                                    input_scale=iscale, dcoeff=0.0, dlogscale=0.0))
+        e["dcoeff"] += g[2 * t] * pair_coeff       # term coefficient = pair_coeff * kc
+        e["dlogscale"] += g[2 * t + 1]
+    noise = float(qd.sum()) if np.ndim(fx.noise) == 0 else qd
+    return LogpdfGradient(noise, list(agg.values()))
+
+
+def save_factor(fx: "FiniteGP") -> np.ndarray:
+    """Checkpoint the device-resident Cholesky factor of `fx`."""
+    return fx.factor().export()
+
+
+def load_factor(fx: "FiniteGP", blob: np.ndarray) -> "FiniteGP":
+    """Resume: install a checkpointed factor into `fx` (same prior, inputs and noise as when saved)
+    instead of re-assembling and re-factorising."""
+    if fx.post is not None:
+        raise NotImplementedError("load_factor: prior FiniteGPs only")
+    fx._factor = _Factor.load(blob, len(fx))
+    return fx
 
 
 # -- statistics --------------------------------------------------------------------------------

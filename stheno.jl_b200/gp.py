@@ -481,6 +481,7 @@ class SpecBuilder:
         self.dims: list[int] = []
         self._cache: dict = {}
         self.terms: list[tuple] = []
+        self.term_meta: list[tuple] = []
         self.blocks: list[tuple] = []
 
     def _input(self, z, scale):
@@ -510,7 +511,10 @@ class SpecBuilder:
             for b in lt_cols:
                 if not a.same_leaf(b):
                     continue  # independent leaves: zeros (atomic_gp.jl:36-38)
-                for (kc, kid, param, iscale) in a.atom.gp.kernel.lowered():
+                for ci, (kc, kid, param, iscale) in enumerate(a.atom.gp.kernel.lowered()):
+                    # gradient bookkeeping: which leaf / kernel component this term belongs to and the
+                    # factor its coefficient carries besides the component's own multiplier kc
+                    self.term_meta.append((a.atom, a.key, ci, kid, a.coeff * b.coeff, kc, iscale))
                     zl = self._input(a.z, iscale)
                     zr = self._input(b.z, iscale)
                     if self.dims[zl] != self.dims[zr]:
@@ -540,6 +544,7 @@ class SpecBuilder:
         spec.nterms, spec.terms = len(self.terms), terms
         spec.nblocks, spec.blocks = len(self.blocks), blocks
         spec._keep = (arrs, terms, blocks, self.arrays, getattr(self, "_keep", None))
+        spec._meta = self.term_meta
         return spec
 
 

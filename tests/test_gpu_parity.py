@@ -505,3 +505,86 @@ def test_tcgen05_ozaki_gppp_badly_scaled_rows(sb, orc, ozaki_ctx):
     lp, lpo = sb.logpdf(fs(bs, noise), y), orc.logpdf(fo(bo, noise), y)
     assert ozaki_ctx.timings()["trailing_int8_ops"] > 0
     assert abs(lp - lpo) <= 1e-9 * abs(lpo), (lp, lpo)
+
+
+def test_factor_export_import_roundtrip(sb, orc):
+    """Checkpoint / resume of the device-resident factor: an imported handle must
+    reproduce logpdf and the posterior bit for bit."""
+    rng = np.random.default_rng(51)
+    n = 1500
+    x, xs = rng.uniform(0, 40, n), rng.uniform(0, 40, 64)
+    y = np.sin(x) + 0.3 * rng.standard_normal(n)
+    f = sb.gppp(lambda GP: dict(f=GP(sb.Matern32Kernel())))
+    fx = f(sb.GPPPInput("f", x), 0.1)
+    lp = sb.logpdf(fx, y)
+    post = sb.posterior(fx, y)
+    m, v = sb.mean_and_var(post, sb.GPPPInput("f", xs))
+    blob = sb.save_factor(fx)
+    assert blob.dtype == np.uint8 and blob.size > n * (n + 128) // 2 * 8
+    fx2 = sb.load_factor(f(sb.GPPPInput("f", x), 0.1), blob.copy())
+    assert sb.logpdf(fx2, y) == lp
+    m2, v2 = sb.mean_and_var(sb.posterior(fx2, y), sb.GPPPInput("f", xs))
+    np.testing.assert_array_equal(m2, m)
+    np.testing.assert_array_equal(v2, v)
+    with pytest.raises(sb.SthenoB200Error):
+        sb.load_factor(f(sb.GPPPInput("f", x), 0.1), blob[:1000].copy())
+
+
+def test_logpdf_gradients_vs_finite_differences(sb, orc):
+    """d logpdf / d (kernel variances, lengthscales, noise) from the device
+    (1/2 tr((aa' - K^-1) dK)) against central finite differences of the ORACLE's logpdf
+    (the reference checks AD against FiniteDifferences at 1e-4, test/affine_transformations/test_util.jl:31)."""
+    rng = np.random.default_rng(61)
+    x3, x1 = rng.uniform(0, 10, 300), rng.uniform(0, 10, 220)
+    y = rng.standard_normal(520)
+
+    def build(m, th):
+        v1, l1, v2, l2 = th[:4]
+        def mk(GP):
+            f1 = GP(v1 * m.with_lengthscale(m.SEKernel(), l1))
+            f2 = GP(v2 * m.with_lengthscale(m.Matern52Kernel(), l2) + 0.05 * m.WhiteKernel())
+            return dict(f1=f1, f2=f2, f3=f1 + 0.5 * f2)
+        return m.gppp(mk)
+
+    def obs(m):
+        return m.BlockData(m.GPPPInput("f3", x3), m.GPPPInput("f1", x1))
+
+    th = np.array([1.3, 0.8, 0.6, 1.7, 0.15])
+    fs = build(sb, th)
+    gr = sb.grad_logpdf(fs(obs(sb), th[4]), y)
+    f1, f2 = fs.fs["f1"], fs.fs["f2"]
+    k1, k2 = gr.for_atom(f1, 0), gr.for_atom(f2, 0)
+    got = np.array([k1["dcoeff"], -k1["dlogscale"] / th[1], k2["dcoeff"], -k2["dlogscale"] / th[3], gr.noise])
+
+    def lp(t):
+        return orc.logpdf(build(orc, t)(obs(orc), t[4]), y)
+
+    fd = np.zeros(5)
+    for i in range(5):
+        h = 1e-5 * th[i]
+        tp, tmn = th.copy(), th.copy()
+        tp[i] += h
+        tmn[i] -= h
+        fd[i] = (lp(tp) - lp(tmn)) / (2 * h)
+    np.testing.assert_allclose(got, fd, rtol=1e-5, atol=1e-6)
+    # White component of f2: d/d(its multiplier); vector noise: per-observation derivative
+    kw = gr.for_atom(f2, 1)
+    hw = 1e-6
+
+    def lpw(wv):
+        def mk(GP):
+            f1 = GP(th[0] * orc.with_lengthscale(orc.SEKernel(), th[1]))
+            f2 = GP(th[2] * orc.with_lengthscale(orc.Matern52Kernel(), th[3]) + wv * orc.WhiteKernel())
+            return dict(f1=f1, f2=f2, f3=f1 + 0.5 * f2)
+        return orc.logpdf(orc.gppp(mk)(obs(orc), th[4]), y)
+
+    np.testing.assert_allclose(kw["dcoeff"], (lpw(0.05 + hw) - lpw(0.05 - hw)) / (2 * hw), rtol=1e-5)
+    nv = rng.uniform(0.1, 0.3, 520)
+    gv = sb.grad_logpdf(fs(obs(sb), nv), y)
+    i0 = 17
+    nvp, nvm = nv.copy(), nv.copy()
+    nvp[i0] += 1e-6
+    nvm[i0] -= 1e-6
+    fo = build(orc, th)
+    fdv = (orc.logpdf(fo(obs(orc), nvp), y) - orc.logpdf(fo(obs(orc), nvm), y)) / 2e-6
+    np.testing.assert_allclose(gv.noise[i0], fdv, rtol=1e-5)

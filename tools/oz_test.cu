@@ -117,7 +117,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(h1.data(), pr.A1, tot * 8, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(h0.data(), pr.A2, tot * 8, cudaMemcpyDeviceToHost));  // original C
 
-        launch_oz_slice(pr.dPt, nseg, 0, Np, pr.scale, pr.expo, pr.planes, st);
+        launch_oz_slice(oz_src_tiled(Pt, nseg), nseg - 1, pr.nblk - nseg, (int64_t)NB, Np, pr.scale, pr.expo, pr.planes, st);
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         // check the digit planes of one row against the CPU
@@ -138,8 +138,9 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&dbg, 7 * 128 * 64 * 4));
 
         struct Variant { const char* name; int tma_mode; int lbo_override; int sbo_override; };
-        Variant vars[] = {{"sw64 default", 0, -1, -1}, {"sw64 lbo=0", 0, 0, -1}, {"interleave default", 1, -1, -1},
-                          {"interleave lbo<->sbo swapped", 1, -2, -2}};
+        // (round 2: all three encodings below reproduce the CPU digit products exactly on B200; the
+        //  LBO field is indeed ignored for swizzled K-major operands)
+        Variant vars[] = {{"sw64 x2 stages", 0, -1, -1}, {"sw32 x5 stages", 2, -1, -1}, {"interleave default", 1, -1, -1}};
         for (auto& v : vars) {
             CK(cudaMemcpy(pr.A2, h0.data(), tot * 8, cudaMemcpyHostToDevice));
             CK(cudaMemset(dbg, 0xff, 7 * 128 * 64 * 4));
@@ -216,12 +217,12 @@ int main(int argc, char** argv) {
             printf("[time] Np=%lld DMMA   %.3f ms  %.2f TFLOP/s\n", (long long)NpT, ms, flops / ms * 1e-9);
         }
         cudaEventRecord(e0, st);
-        launch_oz_slice(pr.dPt, nseg, 0, NpT, pr.scale, pr.expo, pr.planes, st);
+        launch_oz_slice(oz_src_tiled(Pt, nseg), nseg - 1, pr.nblk - nseg, (int64_t)NB, NpT, pr.scale, pr.expo, pr.planes, st);
         cudaEventRecord(e1, st);
         CK(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&ms, e0, e1);
         printf("[time] slice kernels %.3f ms\n", ms);
-        for (int mode = 0; mode < 2; mode++) {
+        for (int mode = 0; mode <= 2; mode += 2) {
             OzMaps maps; OzDesc d;
             if (oz_make_maps(pr.planes, NpT, mode, &maps)) { printf("map fail\n"); continue; }
             oz_default_desc(&d, mode);
