@@ -30,10 +30,10 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 using namespace sb;
 
 #ifndef SB_DEFAULT_TRAILING
-#define SB_DEFAULT_TRAILING 0
+#define SB_DEFAULT_TRAILING 1   /* tcgen05 int8 Ozaki trailing update (SB_TRAILING=dmma selects the fp64 DMMA path) */
 #endif
 #ifndef SB_DEFAULT_OZ_MODE
-#define SB_DEFAULT_OZ_MODE 0
+#define SB_DEFAULT_OZ_MODE 8   /* SWIZZLE_64B operands, 2 x 84 KB stages, paired N=128 MMAs (fastest measured) */
 #endif
 
 // NCCL is bound lazily with dlopen (only when world > 1): a single-GPU / Julia user never loads
@@ -97,6 +97,7 @@ struct sb_ctx {
     int trailing_mode = 0;   // 0: fp64 DMMA (mma.sync), 1: tcgen05 int8 Ozaki slices (ozaki.cu)
     int num_sms = 148;
     int oz_mode = SB_DEFAULT_OZ_MODE;  // SB_OZ_MODE=0|2
+    int sweep_variant = 0;      // SB_SOLVE=a|b: persistent sweep variant (solve.cu)
     bool legacy_solve = false;  // SB_SOLVE=legacy: two launches per block instead of the persistent sweep
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // caching device allocator: the factor (17 GB at N=65536) and the posterior workspace are
@@ -167,6 +168,11 @@ struct sb_factor {
     double* oz_scale[2] = {nullptr, nullptr};
     int* oz_expo[2] = {nullptr, nullptr};
     unsigned* sweep_flags = nullptr;     // 2*nblk flags of the persistent triangular sweep
+    // logpdf(fx, y) followed by posterior(fx, y) is THE usage pattern (README.md:61-81): the forward
+    // sweep v = L^{-1} delta of the last single-RHS logpdf is kept so posterior only adds the backward one
+    double* vcache = nullptr;            // [2][Np]: delta, then v
+    int* vcache_flag = nullptr;
+    bool vcache_valid = false;
     OzMaps oz_maps[2];
     OzDesc oz_desc;
     int oz_mode = 0;   // TMA / pipeline variant of the tcgen05 kernel (ozaki.cu: 0 = SW64 x 2 stages, 2 = SW32 x 5 stages)
@@ -589,6 +595,11 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     return SB_OK;
 }
 
+__global__ void vec_differs_kernel(const double* a, const double* b, int64_t n, int* flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && __double_as_longlong(a[i]) != __double_as_longlong(b[i])) *flag = 1;
+}
+
 // info = first failing pivot over all ranks (0 = ok): min over ranks of (info ? info : INT64_MAX),
 // mapped on the device -- one tiny all-reduce, no host round trip.
 __global__ void info_map_kernel(long long* info, int back) {
@@ -614,7 +625,7 @@ void forward_solve(sb_ctx* c, sb_factor* f, double* b, int S) {
         int s = S - s0 < 8 ? S - s0 : 8;
         double* bb = b + (int64_t)s0 * f->Np;
         if (!c->legacy_solve) {
-            launch_sweep(f->L, f->invL, bb, s, false, f->sweep_flags, c->num_sms, c->stream);
+            launch_sweep(f->L, f->invL, bb, s, false, f->sweep_flags, c->num_sms, c->stream, c->sweep_variant);
             continue;
         }
         for (int64_t k = 0; k < nblk; k++) {
@@ -631,7 +642,7 @@ void backward_solve(sb_ctx* c, sb_factor* f, double* b, int S) {
         int s = S - s0 < 8 ? S - s0 : 8;
         double* bb = b + (int64_t)s0 * f->Np;
         if (!c->legacy_solve) {
-            launch_sweep(f->L, f->invL, bb, s, true, f->sweep_flags, c->num_sms, c->stream);
+            launch_sweep(f->L, f->invL, bb, s, true, f->sweep_flags, c->num_sms, c->stream, c->sweep_variant);
             continue;
         }
         for (int64_t k = nblk - 1; k >= 0; k--) {
@@ -677,9 +688,10 @@ int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
     if (ft && ft[0] == '0') c->fine_timing = false;
     SB_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
     const char* om = getenv("SB_OZ_MODE");
-    if (om && (om[0] == '0' || om[0] == '2')) c->oz_mode = om[0] - '0';
+    if (om) { int m = atoi(om); if (m == 0 || m == 2 || m == 4 || m == 6 || m == 8 || m == 10 || m == 16) c->oz_mode = m; }
     const char* sv = getenv("SB_SOLVE");
     c->legacy_solve = sv && !strcmp(sv, "legacy");
+    c->sweep_variant = (sv && !strcmp(sv, "b")) ? 1 : 0;
     const char* tr = getenv("SB_TRAILING");   // "dmma" | "ozaki"
     c->trailing_mode = SB_DEFAULT_TRAILING;
     if (tr && !strcmp(tr, "dmma")) c->trailing_mode = 0;
@@ -743,6 +755,8 @@ int32_t sb_ctx_set_option(sb_ctx* c, const char* key, int64_t value) {
         return SB_OK;
     }
     if (!strcmp(key, "fine_timing")) { c->fine_timing = value != 0; return SB_OK; }
+    if (!strcmp(key, "sweep_variant")) { c->sweep_variant = (int)value; c->legacy_solve = value < 0; return SB_OK; }
+    if (!strcmp(key, "oz_mode")) { c->oz_mode = (int)value; return SB_OK; }
     sb::set_error(std::string("unknown option ") + key);
     return SB_ERR_INVALID;
 }
@@ -832,6 +846,8 @@ int32_t sb_factor_destroy(sb_factor* f) {
         c->pool_release(f->oz_expo[i], (size_t)f->Np * sizeof(int));
     }
     c->pool_release(f->sweep_flags, (size_t)2 * (f->Np / NB) * sizeof(unsigned));
+    c->pool_release(f->vcache, (size_t)2 * f->Np * sizeof(double));
+    c->pool_release(f->vcache_flag, sizeof(int));
     delete f;
     return SB_OK;
 }
@@ -867,6 +883,8 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->panel, f->bytes_panel);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->alpha, f->bytes_alpha);
     if (e == cudaSuccess) e = c->pool_alloc((void**)&f->sweep_flags, (size_t)2 * nblk * sizeof(unsigned));
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->vcache, (size_t)2 * f->Np * sizeof(double));
+    if (e == cudaSuccess) e = c->pool_alloc((void**)&f->vcache_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaMemsetAsync(f->info_dev, 0, sizeof(long long), c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->logdet_blk, 0, nblk * sizeof(double), c->stream);
     // tcgen05 path: worth it (and exercised) once the trailing matrix has a few hundred tiles
@@ -1069,7 +1087,12 @@ int32_t sb_logpdf(sb_ctx* c, sb_factor* f, const void* delta, int32_t S, double*
     SB_TRY(q.alloc(S * sizeof(double)));
     SB_TRY(upload_padded(c, delta, f->N, f->Np, S, b.d()));
     PhaseTimer t(c, &c->tm.solve_ms);
+    if (S == 1) SB_CUDA(cudaMemcpyAsync(f->vcache, b.p, f->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     forward_solve(c, f, b.d(), S);
+    if (S == 1) {
+        SB_CUDA(cudaMemcpyAsync(f->vcache + f->Np, b.p, f->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        f->vcache_valid = true;
+    }
     launch_colsumsq(b.d(), f->Np, f->Np, S, q.d(), c->stream);
     t.stop();
     SB_CUDA(cudaGetLastError());
@@ -1089,7 +1112,18 @@ int32_t sb_factor_set_data(sb_ctx* c, sb_factor* f, const void* delta) {
     int64_t before = g_launch_count;
     SB_TRY(upload_padded(c, delta, f->N, f->Np, 1, f->alpha));
     PhaseTimer t(c, &c->tm.solve_ms);
-    forward_solve(c, f, f->alpha, 1);
+    bool reuse = false;
+    if (f->vcache_valid) {   // same delta as the last logpdf call on this handle?  (bitwise, on device)
+        int h = 1;
+        SB_CUDA(cudaMemsetAsync(f->vcache_flag, 0, sizeof(int), c->stream));
+        vec_differs_kernel<<<(unsigned)((f->Np + 255) / 256), 256, 0, c->stream>>>(f->alpha, f->vcache, f->Np, f->vcache_flag);
+        g_launch_count++;
+        SB_CUDA(cudaMemcpyAsync(&h, f->vcache_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        reuse = h == 0;
+    }
+    if (reuse) SB_CUDA(cudaMemcpyAsync(f->alpha, f->vcache + f->Np, f->Np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    else forward_solve(c, f, f->alpha, 1);
     backward_solve(c, f, f->alpha, 1);
     t.stop();
     SB_CUDA(cudaGetLastError());

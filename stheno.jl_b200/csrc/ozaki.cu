@@ -126,6 +126,41 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// same, with the two 64-bit shared-memory descriptors assembled from a per-operand low word
+// (start address >> 4 | LBO << 16) and a common compile-time high word (SBO | version | layout):
+// the issue loop then costs one 32-bit add per operand, all in the uniform datapath.
+__device__ __forceinline__ void mma_i8_lohi(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                            uint32_t acc) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %5, 0;\n"
+        " mov.b64 da, {%1, %3};\n mov.b64 db, {%2, %3};\n"
+        " tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}"
+        ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// A operand from TMEM (tcgen05.mma ".ts" form): A[128 x 32 B] sits in 8 TMEM columns, lane = row
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                          uint32_t acc) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b64 db;\n setp.ne.b32 p, %5, 0;\n"
+        " mov.b64 db, {%2, %3};\n"
+        " tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// shared memory -> TMEM copy of one 128-row x 256-bit operand slab (same matrix descriptor as the MMA's)
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t dst_tmem, uint32_t slo, uint32_t hi) {
+    asm volatile(
+        "{\n .reg .b64 ds;\n mov.b64 ds, {%1, %2};\n"
+        " tcgen05.cp.cta_group::1.128x256b [%0], ds;\n}"
+        ::"r"(dst_tmem), "r"(slo), "r"(hi)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -204,7 +239,62 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return d;
 }
 
-template <int KC, int STAGES>
+// Epilogue of both kernel variants (warps 0..7): drain the seven int32 accumulators of each tile from
+// TMEM, weight + sum them in fp64 registers, release each accumulator right after its tcgen05.ld, then
+// C -= s_i s_j acc on the fp64 matrix.
+__device__ __forceinline__ void oz_epilogue(const OzArgs& g, uint32_t tmem, uint32_t tfull0, uint32_t tempty0, int warp,
+                                            int lane) {
+        const int lq = warp & 3, ch = warp >> 2;  // TMEM lane quarter (hardware: warp % 4), column half
+        OzCursor cur;
+        cur.init(g, blockIdx.x);
+        uint32_t it = 0;
+        for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x), it++) {
+            const OzTile tl = cur.tile(g);
+            double acc[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) acc[c] = 0.0;
+#pragma unroll
+            for (int grp = 0; grp < OZ_S; grp++) {
+                mbar_wait(tfull0 + 8 * grp, it & 1);
+                tc_fence_after();
+                int v[32];
+                tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + ch * 32), v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * grp);   // accumulator may be overwritten
+                const double wt = (double)(1ull << (8 * (OZ_S - 1 - grp)));   // 2^(8(8 - t)), t = grp + 2
+                if (g.dbg != nullptr && cur.t == 0) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) g.dbg[(grp * OZ_BM + lq * 32 + lane) * OZ_BN + ch * 32 + c] = v[c];
+                }
+#ifndef OZ_ABLATE_NO_CVT
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[c] = fma((double)v[c], wt, acc[c]);
+#else
+                acc[grp] += (double)v[grp] * wt;   // timing experiment: no per-element int -> fp64 work
+#endif
+            }
+            // C[rows lq*32 + lane, cols ch*32 .. +32 of the tile] -= s_i s_j acc
+            const int64_t ldc = tl.ldc;
+            const int row = lq * 32 + lane;
+            double* cp = tl.C + (int64_t)(ch * 32) * ldc + row;
+            const double si = g.scaleA[tl.rowA + row];
+            const double* sj = g.scaleB + tl.rowB + ch * 32;
+#ifdef OZ_ABLATE_NO_C
+            continue;
+#endif
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+                double old[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) old[c] = __ldcs(cp + (int64_t)(c0 + c) * ldc);
+#pragma unroll
+                for (int c = 0; c < 8; c++) cp[(int64_t)(c0 + c) * ldc] = fma(-(si * sj[c0 + c]), acc[c0 + c], old[c]);
+            }
+        }
+}
+
+template <int KC, int STAGES, int TMODE, bool ATMEM, bool PAIR>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUtensorMap tmA,
                   const __grid_constant__ CUtensorMap tmB) {
@@ -212,6 +302,14 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
     constexpr int OZ_STAGES = STAGES, OZ_KC = KC;
     constexpr int OZ_A_PLANE = Cfg::A_PLANE, OZ_B_PLANE = Cfg::B_PLANE, OZ_A_STAGE = Cfg::A_STAGE;
     constexpr int OZ_STAGE_BYTES = Cfg::STAGE_BYTES;
+    // shared-memory matrix descriptor constants of the operand layout (see oz_default_desc):
+    //   TMODE 0: K-major SWIZZLE_64B rows of 64 B; 2: SWIZZLE_32B rows of 32 B; 1: un-swizzled interleave
+    constexpr uint32_t D_LAYOUT = TMODE == 0 ? 4u : (TMODE == 2 ? 6u : 0u);
+    constexpr uint32_t D_SBO = TMODE == 0 ? 32u : (TMODE == 2 ? 16u : 8u);
+    constexpr uint32_t D_LBO_A = TMODE == 1 ? (OZ_BM * 16 >> 4) : 1u, D_LBO_B = TMODE == 1 ? (OZ_BN * 16 >> 4) : 1u;
+    constexpr uint32_t D_KK_A = TMODE == 0 ? 2u : (TMODE == 1 ? 2u * (OZ_BM * 16 >> 4) : 0u);
+    constexpr uint32_t D_KK_B = TMODE == 0 ? 2u : (TMODE == 1 ? 2u * (OZ_BN * 16 >> 4) : 0u);
+    constexpr uint32_t D_HI = D_SBO | (1u << 14) | (D_LAYOUT << 29);
     extern __shared__ unsigned char oz_smem_raw[];
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // stage buffers: 1024-byte aligned
@@ -258,6 +356,9 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                 const int rowA = tl.rowA, rowB = tl.rowB;
                 for (int kc = 0; kc < g.kchunks; kc++, n++) {
                     const uint32_t st = n % OZ_STAGES, ph = (n / OZ_STAGES) & 1;
+#ifdef OZ_ABLATE_NO_TMA
+                    continue;
+#endif
                     mbar_wait(empty0 + 8 * st, ph ^ 1);
                     const uint32_t fb = full0 + 8 * st;
                     mbar_expect_tx(fb, OZ_STAGE_BYTES);
@@ -274,20 +375,59 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            // instruction descriptor, kind::i8: D = S32 (2 @ [4,6)), A = B = INT8 (1 @ [7,10), [10,13)),
-            // K-major both, N >> 3 @ [17,23), M >> 4 @ [24,29)
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
+        // The whole warp runs this (warp-uniform) loop so the address arithmetic stays in the uniform
+        // datapath; one elected lane issues.  Measured (round 2): with per-MMA 64-bit descriptor
+        // arithmetic in a single divergent lane the kernel was ISSUE-bound (tensor pipe 39 % active).
+        const bool leader = elect_one();
+        // instruction descriptor, kind::i8: D = S32 (2 @ [4,6)), A = B = INT8 (1 @ [7,10), [10,13)),
+        // K-major both, N >> 3 @ [17,23), M >> 4 @ [24,29)
+        constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
                                    ((uint32_t)(OZ_BM >> 4) << 24);
-            uint32_t n = 0, it = 0;
-            for (int64_t t = blockIdx.x; t < g.total_tiles; t += gridDim.x, it++) {
-                for (int kc = 0; kc < g.kchunks; kc++, n++) {
-                    const uint32_t st = n % OZ_STAGES, ph = (n / OZ_STAGES) & 1;
-                    mbar_wait(full0 + 8 * st, ph);
-                    tc_fence_after();
-                    const uint32_t sA = base + st * OZ_STAGE_BYTES, sB = sA + OZ_A_STAGE;
-                    const uint64_t dA0 = make_desc(sA, g.a_lbo, g.sbo, g.layout);
-                    const uint64_t dB0 = make_desc(sB, g.b_lbo, g.sbo, g.layout);
+        uint32_t n = 0, it = 0;
+        for (int64_t t = blockIdx.x; t < g.total_tiles; t += gridDim.x, it++) {
+            for (int kc = 0; kc < g.kchunks; kc++, n++) {
+                const uint32_t st = n % OZ_STAGES, ph = (n / OZ_STAGES) & 1;
+#ifndef OZ_ABLATE_NO_TMA
+                mbar_wait(full0 + 8 * st, ph);
+#endif
+                tc_fence_after();
+                const uint32_t sA = base + st * OZ_STAGE_BYTES, sB = sA + OZ_A_STAGE;
+                const uint32_t a0 = (sA >> 4) | (D_LBO_A << 16), b0 = (sB >> 4) | (D_LBO_B << 16);
+                const uint32_t acc0 = kc > 0 ? 1u : 0u;
+                if constexpr (PAIR) {
+                    // Two digit planes of B per instruction.  Measured (round 2, tools/oz_test ablations): an
+                    // M=128 N=64 K=32 int8 MMA takes ~71 clk however its operands are fed (smem or TMEM), i.e.
+                    // the instruction has a ~64 clk floor and N=64 runs the tensor pipe at half rate.  The B
+                    // planes q and q+1 are adjacent in shared memory with the same row-group stride, so ONE
+                    // N=128 instruction computes A_p B_q^T and A_p B_{q+1}^T into the adjacent accumulators of
+                    // groups p+q and p+q+1: 16 instructions per K=32 step instead of 28.
+                    constexpr uint32_t idesc128 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * OZ_BN >> 3) << 17) |
+                                                  ((uint32_t)(OZ_BM >> 4) << 24);
+#pragma unroll
+                    for (int kk = 0; kk < OZ_KC / 32; kk++) {
+#pragma unroll
+                        for (int p = 0; p < OZ_S; p++) {
+#pragma unroll
+                            for (int q = 0; q < OZ_S - p; q += 2) {
+                                const bool two = (q + 1 < OZ_S - p);
+                                if (kc == 0 && kk == 0 && p == 0) {   // first touch of group(s) q (and q+1) in this tile
+                                    mbar_wait(tempty0 + 8 * q, (it & 1) ^ 1);
+                                    if (two) mbar_wait(tempty0 + 8 * (q + 1), (it & 1) ^ 1);
+                                    tc_fence_after();
+                                }
+                                const uint32_t alo = a0 + (uint32_t)(p * (OZ_A_PLANE >> 4)) + (uint32_t)kk * D_KK_A;
+                                const uint32_t blo = b0 + (uint32_t)(q * (OZ_B_PLANE >> 4)) + (uint32_t)kk * D_KK_B;
+                                if (leader)
+                                    mma_i8_lohi(tmem + (uint32_t)(p + q) * OZ_BN, alo, blo, D_HI, two ? idesc128 : idesc,
+                                                (p > 0 || kk > 0) ? 1u : acc0);
+                            }
+                        }
+                    }
+                    if (kc == g.kchunks - 1 && leader) {
+#pragma unroll
+                        for (int grp = 0; grp < OZ_S; grp++) tc_commit(tfull0 + 8 * grp);
+                    }
+                } else if constexpr (!ATMEM) {
 #pragma unroll
                     for (int grp = 0; grp < OZ_S; grp++) {         // grp = p + q - 2
                         if (kc == 0) {                              // accumulator must have been drained
@@ -300,60 +440,187 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                             const int q = grp - p;
 #pragma unroll
                             for (int kk = 0; kk < OZ_KC / 32; kk++) {
-                                const uint64_t da = dA0 + (uint64_t)(p * (OZ_A_PLANE >> 4) + kk * g.a_kk_adv);
-                                const uint64_t db = dB0 + (uint64_t)(q * (OZ_B_PLANE >> 4) + kk * g.b_kk_adv);
-                                mma_i8(d, da, db, idesc, (kc > 0 || p > 0 || kk > 0) ? 1u : 0u);
+                                const uint32_t alo = a0 + (uint32_t)(p * (OZ_A_PLANE >> 4)) + (uint32_t)kk * D_KK_A;
+                                const uint32_t blo = b0 + (uint32_t)(q * (OZ_B_PLANE >> 4)) + (uint32_t)kk * D_KK_B;
+#ifndef OZ_ABLATE_NO_MMA
+                                if (leader) mma_i8_lohi(d, alo, blo, D_HI, idesc, (p > 0 || kk > 0) ? 1u : acc0);
+#endif
                             }
                         }
-                        if (kc == g.kchunks - 1) tc_commit(tfull0 + 8 * grp);   // G_{grp+2} of this tile is final
+                        if (kc == g.kchunks - 1 && leader) tc_commit(tfull0 + 8 * grp);   // G_{grp+2} of this tile is final
                     }
-                    tc_commit(empty0 + 8 * st);  // smem stage free once these MMAs have read it
+                } else {
+                    // A operand through TMEM: the 7 digit planes of one K = 32 step are copied smem -> TMEM
+                    // once (tcgen05.cp, 8 columns each, columns 448..503) and every MMA of the step then
+                    // reads only B from shared memory: 2 KB instead of 6 KB per MMA.  In SS mode the kernel
+                    // is shared-memory-bandwidth bound (ncu: 83 % of the smem pipe, 72 clk per N=64 MMA whose
+                    // tensor floor is 32 clk).  tcgen05.cp and tcgen05.mma execute in issue order, so the
+                    // next step's copies cannot overtake the MMAs still reading the slab.
+                    constexpr uint32_t A_TMEM_COL = OZ_S * OZ_BN;   // 448
+#pragma unroll
+                    for (int kk = 0; kk < OZ_KC / 32; kk++) {
+#pragma unroll
+                        for (int p = 0; p < OZ_S; p++) {
+                            const uint32_t alo = a0 + (uint32_t)(p * (OZ_A_PLANE >> 4)) + (uint32_t)kk * D_KK_A;
+                            if (leader) tmem_cp_128x256b(tmem + A_TMEM_COL + (uint32_t)p * 8, alo, D_HI);
+                        }
+#pragma unroll
+                        for (int grp = 0; grp < OZ_S; grp++) {
+                            if (kc == 0 && kk == 0) {
+                                mbar_wait(tempty0 + 8 * grp, (it & 1) ^ 1);
+                                tc_fence_after();
+                            }
+                            const uint32_t d = tmem + (uint32_t)grp * OZ_BN;
+#pragma unroll
+                            for (int p = 0; p <= grp; p++) {
+                                const int q = grp - p;
+                                const uint32_t blo = b0 + (uint32_t)(q * (OZ_B_PLANE >> 4)) + (uint32_t)kk * D_KK_B;
+                                if (leader)
+                                    mma_i8_ts(d, tmem + A_TMEM_COL + (uint32_t)p * 8, blo, D_HI, idesc,
+                                              (p > 0 || kk > 0) ? 1u : acc0);
+                            }
+                            if (kc == g.kchunks - 1 && kk == OZ_KC / 32 - 1 && leader) tc_commit(tfull0 + 8 * grp);
+                        }
+                    }
                 }
+#ifndef OZ_ABLATE_NO_TMA
+                if (leader) tc_commit(empty0 + 8 * st);  // smem stage free once these MMAs have read it
+#endif
+                __syncwarp();
             }
         }
     } else {
         // ===================== epilogue warps 0..7 =====================
-        const int lq = warp & 3, ch = warp >> 2;  // TMEM lane quarter (hardware: warp % 4), column half
-        OzCursor cur;
-        cur.init(g, blockIdx.x);
-        uint32_t it = 0;
-        for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x), it++) {
-            const OzTile tl = cur.tile(g);
-            double acc[32];
-#pragma unroll
-            for (int c = 0; c < 32; c++) acc[c] = 0.0;
-#pragma unroll
-            for (int grp = 0; grp < OZ_S; grp++) {
-                mbar_wait(tfull0 + 8 * grp, it & 1);
-                tc_fence_after();
-                int v[32];
-                tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + ch * 32), v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * grp);   // accumulator may be overwritten
-                const double wt = (double)(1ull << (8 * (OZ_S - 1 - grp)));   // 2^(8(8 - t)), t = grp + 2
-                if (g.dbg != nullptr && cur.t == 0) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++) g.dbg[(grp * OZ_BM + lq * 32 + lane) * OZ_BN + ch * 32 + c] = v[c];
+        oz_epilogue(g, tmem, tfull0, tempty0, warp, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// ---- ring-pipelined variant (the one that ships) ---------------------------------------------------
+// Measured on B200 (tools/mb_tcgen05, tools/oz_test ablations, profiles/): an M=128 N=64 K=32 int8 MMA
+// with both operands in shared memory takes 48 clk (smem-bound: 6 KB of operands per instruction), N=128
+// takes 64 clk = the 4.57 POP/s peak; the TMA path delivers ~80 GB/s per SM (8.6 us for the 688 KB of a
+// tile) with ~2 us latency, so the 2 x 84 KB stage ring above can keep at most ONE stage in flight and the
+// MMA and TMA times ADD (15.8 us per tile instead of max(7.8, 8.6)).  Here the ring is fine-grained:
+//   * B (7 planes x 64 rows x 64 B = 28 KB per k-chunk) is double-buffered,
+//   * A streams plane by plane (128 rows x 64 B = 8 KB) through a deep ring of RING_A slots, each with
+//     its own full/empty mbarrier: the MMA warp consumes plane p while planes p+1.. of this and the next
+//     k-chunks are still landing -- ~170 KB in flight instead of 84 KB,
+//   * MMAs are issued per A plane against PAIRS of adjacent B planes (N = 128: two accumulators at once).
+constexpr int RING_A = 18;           // A-plane slots of 8 KB
+constexpr int RING_B = 2;            // B stages of 28 KB
+constexpr int RK = 64;               // bytes of K per chunk (SWIZZLE_64B rows)
+constexpr int RA_SLOT = OZ_BM * RK;  // 8192
+constexpr int RB_PLANE = OZ_BN * RK; // 4096
+constexpr int RB_STAGE = OZ_S * RB_PLANE;  // 28672
+constexpr size_t RING_SMEM = (size_t)RING_B * RB_STAGE + (size_t)RING_A * RA_SLOT + 1024 + 8 * (2 * RING_A + 2 * RING_B + 2 * OZ_S) + 64;
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_ring_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB) {
+    constexpr uint32_t D_HI = 32u | (1u << 14) | (4u << 29);   // SBO 512 B, version 1, SWIZZLE_64B
+    extern __shared__ unsigned char oz_smem_raw[];
+    const uint32_t raw = smem_u32(oz_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sB0 = base, sA0 = base + RING_B * RB_STAGE;
+    const uint32_t bars = sA0 + RING_A * RA_SLOT;
+    const uint32_t fullA = bars, emptyA = fullA + 8 * RING_A, fullB = emptyA + 8 * RING_A, emptyB = fullB + 8 * RING_B,
+                   tfull0 = emptyB + 8 * RING_B, tempty0 = tfull0 + 8 * OZ_S, tmem_slot = tempty0 + 8 * OZ_S;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(oz_smem_raw + (tmem_slot - raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < RING_A; i++) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
+        for (int i = 0; i < RING_B; i++) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
+        for (int t = 0; t < OZ_S; t++) { mbar_init(tfull0 + 8 * t, 1); mbar_init(tempty0 + 8 * t, OZ_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            OzCursor cur;
+            cur.init(g, blockIdx.x);
+            uint32_t na = 0, nb = 0;
+            for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x)) {
+                const OzTile tl = cur.tile(g);
+                for (int kc = 0; kc < g.kchunks; kc++, nb++) {
+                    {
+                        const uint32_t bs = nb % RING_B, ph = (nb / RING_B) & 1;
+                        mbar_wait(emptyB + 8 * bs, ph ^ 1);
+                        mbar_expect_tx(fullB + 8 * bs, RB_STAGE);
+                        tma_load_3d(sB0 + bs * RB_STAGE, &tmB, kc * RK, tl.rowB, 0, fullB + 8 * bs);
+                    }
+#pragma unroll 1
+                    for (int p = 0; p < OZ_S; p++, na++) {
+                        const uint32_t sl = na % RING_A, ph = (na / RING_A) & 1;
+                        mbar_wait(emptyA + 8 * sl, ph ^ 1);
+                        mbar_expect_tx(fullA + 8 * sl, RA_SLOT);
+                        tma_load_3d(sA0 + sl * RA_SLOT, &tmA1, kc * RK, tl.rowA, p, fullA + 8 * sl);
+                    }
                 }
-#pragma unroll
-                for (int c = 0; c < 32; c++) acc[c] = fma((double)v[c], wt, acc[c]);
-            }
-            // C[rows lq*32 + lane, cols ch*32 .. +32 of the tile] -= s_i s_j acc
-            const int64_t ldc = tl.ldc;
-            const int row = lq * 32 + lane;
-            double* cp = tl.C + (int64_t)(ch * 32) * ldc + row;
-            const double si = g.scaleA[tl.rowA + row];
-            const double* sj = g.scaleB + tl.rowB + ch * 32;
-#pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 8) {
-                double old[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) old[c] = __ldcs(cp + (int64_t)(c0 + c) * ldc);
-#pragma unroll
-                for (int c = 0; c < 8; c++) cp[(int64_t)(c0 + c) * ldc] = fma(-(si * sj[c0 + c]), acc[c0 + c], old[c]);
             }
         }
+    } else if (warp == 9) {
+        // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) ==========
+        const bool leader = elect_one();
+        constexpr uint32_t idesc64 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+        constexpr uint32_t idesc128 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+        uint32_t na = 0, nb = 0, it = 0;
+        for (int64_t t = blockIdx.x; t < g.total_tiles; t += gridDim.x, it++) {
+            for (int kc = 0; kc < g.kchunks; kc++, nb++) {
+                const uint32_t bs = nb % RING_B;
+                mbar_wait(fullB + 8 * bs, (nb / RING_B) & 1);
+                const uint32_t b0 = ((sB0 + bs * RB_STAGE) >> 4) | (1u << 16);
+                const uint32_t acc0 = kc > 0 ? 1u : 0u;
+#pragma unroll
+                for (int p = 0; p < OZ_S; p++, na++) {
+                    const uint32_t sl = na % RING_A;
+                    mbar_wait(fullA + 8 * sl, (na / RING_A) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = ((sA0 + sl * RA_SLOT) >> 4) | (1u << 16);
+#pragma unroll
+                    for (int kk = 0; kk < RK / 32; kk++) {
+#pragma unroll
+                        for (int q = 0; q < OZ_S - p; q += 2) {
+                            const bool two = (q + 1 < OZ_S - p);
+                            if (kc == 0 && kk == 0 && p == 0) {   // first touch of group(s) q (and q+1) in this tile
+                                mbar_wait(tempty0 + 8 * q, (it & 1) ^ 1);
+                                if (two) mbar_wait(tempty0 + 8 * (q + 1), (it & 1) ^ 1);
+                                tc_fence_after();
+                            }
+                            if (leader)
+                                mma_i8_lohi(tmem + (uint32_t)(p + q) * OZ_BN, a0 + (uint32_t)kk * 2u,
+                                            b0 + (uint32_t)(q * (RB_PLANE >> 4)) + (uint32_t)kk * 2u, D_HI,
+                                            two ? idesc128 : idesc64, (p > 0 || kk > 0) ? 1u : acc0);
+                        }
+                    }
+                    if (leader) tc_commit(emptyA + 8 * sl);     // A plane slot free once these MMAs have read it
+                }
+                if (leader) tc_commit(emptyB + 8 * bs);
+                if (kc == g.kchunks - 1 && leader) {
+#pragma unroll
+                    for (int grp = 0; grp < OZ_S; grp++) tc_commit(tfull0 + 8 * grp);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        oz_epilogue(g, tmem, tfull0, tempty0, warp, lane);
     }
 
     tc_fence_before();
@@ -436,7 +703,10 @@ int g_oz_sms = 0;
 // tma_mode -> (KC, STAGES) instance
 #define OZ_DISPATCH(mode, CALL)                                  \
     do {                                                         \
-        if ((mode) == 2) { CALL(32, 5); } else { CALL(64, 2); }  \
+        if ((mode) == 2) { CALL(32, 5, 2, false, false); } else if ((mode) == 1) { CALL(64, 2, 1, false, false); }       \
+        else if ((mode) == 4) { CALL(64, 2, 0, true, false); } else if ((mode) == 6) { CALL(32, 5, 2, true, false); }     \
+        else if ((mode) == 8) { CALL(64, 2, 0, false, true); } else if ((mode) == 10) { CALL(32, 5, 2, false, true); }    \
+        else { CALL(64, 2, 0, false, false); }                                                                            \
     } while (0)
 
 int oz_init() {
@@ -447,10 +717,14 @@ int oz_init() {
         g_encode = (EncodeTiled_t)fn;
     }
     if (!g_oz_attr) {
-        if (cudaFuncSetAttribute(ozaki_syrk_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)OzCfg<64, 2>::SMEM) != cudaSuccess) return -2;
-        if (cudaFuncSetAttribute(ozaki_syrk_kernel<32, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)OzCfg<32, 5>::SMEM) != cudaSuccess) return -2;
+#define OZ_ATTR(KC, ST, TM, AT, PR)                                                                              \
+        if (cudaFuncSetAttribute(ozaki_syrk_kernel<KC, ST, TM, AT, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)OzCfg<KC, ST>::SMEM) != cudaSuccess) return -2
+        OZ_ATTR(64, 2, 0, false, false); OZ_ATTR(64, 2, 1, false, false); OZ_ATTR(32, 5, 2, false, false);
+        OZ_ATTR(64, 2, 0, true, false); OZ_ATTR(32, 5, 2, true, false);
+        OZ_ATTR(64, 2, 0, false, true); OZ_ATTR(32, 5, 2, false, true);
+        if (cudaFuncSetAttribute(ozaki_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM) != cudaSuccess) return -2;
+#undef OZ_ATTR
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_oz_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -466,10 +740,21 @@ size_t oz_planes_bytes(int64_t Np) { return (size_t)OZ_S * Np * OZ_KMAX; }
 // Build the two tensor maps (A box: 128 rows, B box: 64 rows) over the digit planes.
 int oz_make_maps(signed char* planes, int64_t Np, int tma_mode, OzMaps* out) {
     if (oz_init() != 0) return -1;
+    tma_mode = tma_mode >= 16 ? 0 : (tma_mode & 3);   // bits 2 / 3 / 4 only select kernel variants (A via TMEM / paired N / ring)
     static_assert(sizeof(out->a) >= sizeof(CUtensorMap), "OzMaps too small");
     CUtensorMap* ma = reinterpret_cast<CUtensorMap*>(out->a);
     CUtensorMap* mb = reinterpret_cast<CUtensorMap*>(out->b);
     CUresult r1, r2;
+    {   // single-plane A box of the ring kernel (always built: 128 rows x 64 B x 1 plane, SWIZZLE_64B)
+        CUtensorMap* m1 = reinterpret_cast<CUtensorMap*>(out->a1);
+        cuuint64_t dims[3] = {(cuuint64_t)OZ_KMAX, (cuuint64_t)Np, (cuuint64_t)OZ_S};
+        cuuint64_t strides[2] = {(cuuint64_t)OZ_KMAX, (cuuint64_t)Np * OZ_KMAX};
+        cuuint32_t estr[3] = {1, 1, 1};
+        cuuint32_t box1[3] = {64, OZ_BM, 1};
+        if (g_encode(m1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes, dims, strides, box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -3;
+    }
     if (tma_mode == 0 || tma_mode == 2) {
         const cuuint32_t kc = tma_mode == 0 ? 64 : 32;
         const CUtensorMapSwizzle sw = tma_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -518,6 +803,7 @@ OzSrc oz_src_tiled(const double* const* Pt, int nseg) {
 }
 
 void oz_default_desc(OzDesc* d, int tma_mode) {
+    tma_mode = tma_mode >= 16 ? 0 : (tma_mode & 3);
     if (tma_mode == 0) {
         d->a_kk_adv = d->b_kk_adv = 2;  // +32 bytes inside the 64-byte swizzled row
         d->a_lbo = d->b_lbo = 1;        // unused for swizzled K-major
@@ -551,7 +837,13 @@ static int oz_launch(OzArgs& g, const OzMaps* mapsA, const OzMaps* mapsB, cudaSt
     const int64_t grid = g.total_tiles < cap ? g.total_tiles : cap;
     const CUtensorMap* ma = reinterpret_cast<const CUtensorMap*>(mapsA->a);
     const CUtensorMap* mb = reinterpret_cast<const CUtensorMap*>(mapsB->b);
-#define OZ_LAUNCH(KC, ST) ozaki_syrk_kernel<KC, ST><<<(unsigned)grid, OZ_THREADS, OzCfg<KC, ST>::SMEM, s>>>(g, *ma, *mb)
+    if (g.tma_mode >= 16) {
+        const CUtensorMap* m1 = reinterpret_cast<const CUtensorMap*>(mapsA->a1);
+        ozaki_ring_kernel<<<(unsigned)grid, OZ_THREADS, RING_SMEM, s>>>(g, *m1, *mb);
+        g_launch_count++;
+        return 0;
+    }
+#define OZ_LAUNCH(KC, ST, TM, AT, PR) ozaki_syrk_kernel<KC, ST, TM, AT, PR><<<(unsigned)grid, OZ_THREADS, OzCfg<KC, ST>::SMEM, s>>>(g, *ma, *mb)
     OZ_DISPATCH(g.tma_mode, OZ_LAUNCH);
 #undef OZ_LAUNCH
     g_launch_count++;
@@ -574,7 +866,7 @@ int launch_syrk_ozaki(Packed Apk, int64_t k, int nseg, int64_t jlo, int64_t jhi,
     g.mode = 1;
     g.Pk = Apk; g.J0 = J0; g.w = world;
     g.total_tiles = tiles * 2;
-    g.kchunks = nseg * NB / (tma_mode == 2 ? 32 : 64);
+    g.kchunks = nseg * NB / ((tma_mode < 16 && (tma_mode & 3) == 2) ? 32 : 64);
     g.scaleA = g.scaleB = scale;
     oz_fill_desc(g, desc, tma_mode, dbg);
     return oz_launch(g, maps, maps, s, reserve_sms);
@@ -592,7 +884,7 @@ int launch_gemm_ozaki(double* C, int64_t ldc, int64_t M, int64_t Ncols, int nseg
     g.mode = 0;
     g.C = C; g.ldc = ldc; g.mtiles = M / OZ_BM;
     g.total_tiles = (M / OZ_BM) * (Ncols / OZ_BN);
-    g.kchunks = nseg * NB / (tma_mode == 2 ? 32 : 64);
+    g.kchunks = nseg * NB / ((tma_mode < 16 && (tma_mode & 3) == 2) ? 32 : 64);
     g.scaleA = scaleA; g.scaleB = scaleB;
     g.rowA0 = rowA0; g.rowB0 = rowB0;
     oz_fill_desc(g, desc, tma_mode, nullptr);

@@ -146,7 +146,7 @@ void launch_gemv_below(Packed L, int64_t k, double* b, int S, cudaStream_t s);
 void launch_gemvT_below(Packed L, int64_t k, double* b, int S, cudaStream_t s);
 // one-launch persistent sweep (solve.cu): flags = 2*nblk unsigned scratch
 void launch_sweep(Packed L, const double* invL, double* b, int S, bool backward, unsigned* flags, int num_sms,
-                  cudaStream_t s);
+                  cudaStream_t s, int variant = 0);
 void launch_colsumsq(const double* v, int64_t n, int64_t ld, int S, double* out, cudaStream_t s);
 // y[M] (+)= W[M x n] * a[n]   (W column-major, ld)
 void launch_gemv_n(const double* W, int64_t ld, int64_t M, int64_t n, const double* a, double* y,
@@ -172,7 +172,7 @@ void launch_add_diag(Packed L, const double* d, int64_t n, cudaStream_t st);
 void launch_add_dense_lower(Packed L, const double* D, int64_t ld, int64_t n, cudaStream_t st);
 
 // ---- K3': trailing update on tcgen05 (int8 Ozaki slicing), ozaki.cu ------------------------------
-struct alignas(64) OzMaps { unsigned char a[128]; unsigned char b[128]; };  // two CUtensorMap blobs
+struct alignas(64) OzMaps { unsigned char a[128]; unsigned char b[128]; unsigned char a1[128]; };  // CUtensorMap blobs: A box, B box, single-plane A box
 struct OzDesc { uint32_t a_kk_adv, b_kk_adv, a_lbo, b_lbo, sbo, layout; };
 size_t oz_planes_bytes(int64_t Np);                       // 7 digit planes, 512-byte row pitch
 int oz_make_maps(signed char* planes, int64_t Np, int tma_mode, OzMaps* out);

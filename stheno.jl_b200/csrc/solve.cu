@@ -112,10 +112,11 @@ gemvT_below_kernel(Packed L, int64_t k, double* __restrict__ b, int S) {
 //   backward b <- L^{-T} b :  when x_k = invL_kk^T b_k is final, every block j < k applies
 //                             b_j -= L[k,j]^T x_k.
 // Block i (resp. j) is owned by worker CTA (i mod W) for the whole sweep, so updates of one block
-// are sequential inside one CTA: no atomics on b, bit-reproducible results.  The last CTA only does
-// the diagonal solves; cross-CTA ordering goes through per-block flags (ready[k]: x_k final,
-// done[k]: number of updates applied to b_k) with release/acquire fences; b is read with ld.cg
-// where another SM wrote it.  Each element of L is read exactly once (HBM-bound, 17.2 GB/sweep).
+// are sequential inside one CTA: no atomics on b, bit-reproducible results.  The owner applies the
+// last update of its block and immediately does the diagonal solve, then publishes ready[k]
+// (release/acquire; x_k is read with ld.cg on the other SMs).  The serial chain per block is
+// flag -> x_k -> one 128x128 product with L[k+1,k] -> one with invL_{k+1} -> flag, with both
+// operands prefetched into L2 before the wait.  Each element of L is read once (17.2 GB/sweep).
 struct SweepArgs {
     Packed L;
     const double* invL;
@@ -216,8 +217,11 @@ __device__ __forceinline__ void block_matvec_t(const double* __restrict__ M, int
     __syncthreads();
 }
 
-template <bool BACKWARD>
-__global__ void __launch_bounds__(256) sweep_kernel(SweepArgs a) {
+__device__ __forceinline__ void prefetch_block_l2(const double* M, int64_t ld);
+// variant A: dedicated CTA for the diagonal solves, done[] counters (round-2 measurement: 12-15 ms per
+// sweep at N = 65536; variant B below -- owner does the diagonal solve, L2 prefetch -- measured 23-34 ms)
+template <bool BACKWARD, bool PF>
+__global__ void __launch_bounds__(256) sweep_kernel_a(SweepArgs a) {
     __shared__ double xs[MAXS][NB];
     __shared__ double red[MAXS][NB];
     const int64_t nblk = a.L.nblk(), Np = a.L.Np;
@@ -258,6 +262,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepArgs a) {
         // ---- diagonal solves, in dependency order ----
         for (int64_t kk = 0; kk < nblk; kk++) {
             const int64_t k = BACKWARD ? nblk - 1 - kk : kk;
+            if (PF) prefetch_block_l2(a.invL + k * (int64_t)NB * NB, NB);
             if (threadIdx.x == 0) spin_until(a.done + k, (unsigned)kk);  // all kk updates of b_k applied
             __syncthreads();
             diag_solve(k);
@@ -273,6 +278,10 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepArgs a) {
         int64_t first;
         if (!BACKWARD) { first = k + 1 + (((me - (k + 1)) % W) + W) % W; if (first >= nblk) continue; }
         else           { first = k - 1 - ((((k - 1) - me) % W) + W) % W; if (first < 0) continue; }
+        if (PF) {
+            if (!BACKWARD) prefetch_block_l2(a.L.blk(first, k), a.L.ld(k));
+            else prefetch_block_l2(a.L.blk(k, first), a.L.ld(first));
+        }
         if (threadIdx.x == 0) spin_until(a.ready + k, 1u);
         __syncthreads();
         load_x(k);
@@ -285,6 +294,73 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepArgs a) {
             for (int64_t j = first; j >= 0; j -= W) {
                 update(j, k);
                 if (threadIdx.x == 0) { __threadfence(); red_release_add(a.done + j, 1u); }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void prefetch_block_l2(const double* M, int64_t ld) {
+    // 128 x 128 doubles = 1024 lines of 128 B: 4 per thread
+    for (int idx = threadIdx.x; idx < 1024; idx += 256) {
+        const double* p = M + (int64_t)(idx >> 3) * ld + (idx & 7) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+}
+
+template <bool BACKWARD, bool PF>
+__global__ void __launch_bounds__(256) sweep_kernel_b(SweepArgs a) {
+    __shared__ double xs[MAXS][NB];
+    __shared__ double red[MAXS][NB];
+    const int64_t nblk = a.L.nblk(), Np = a.L.Np;
+    const int S = a.S;
+    const int W = gridDim.x, me = blockIdx.x;
+    auto load_x = [&](int64_t k) {                 // x_k (possibly written by another SM) -> shared memory
+        for (int idx = threadIdx.x; idx < S * NB; idx += 256) {
+            const int s = idx / NB, c = idx % NB;
+            xs[s][c] = __ldcg(a.b + (int64_t)s * Np + k * NB + c);
+        }
+        __syncthreads();
+    };
+    auto diag_solve_publish = [&](int64_t k) {     // b_k is final: x_k = invL_kk b_k (or ^T), then publish
+        load_x(k);
+        const double* Mk = a.invL + k * (int64_t)NB * NB;
+        if (!BACKWARD) block_matvec_n<true>(Mk, NB, xs, a.b + k * NB, Np, S, red);
+        else block_matvec_t<true>(Mk, NB, xs, a.b + k * NB, Np, S);
+        if (threadIdx.x == 0) { __threadfence(); st_release(a.ready + k, 1u); }
+    };
+    auto update = [&](int64_t tgt, int64_t k) {   // block `tgt` absorbs x_k (already in xs)
+        if (!BACKWARD) block_matvec_n<false>(a.L.blk(tgt, k), a.L.ld(k), xs, a.b + tgt * NB, Np, S, red);
+        else block_matvec_t<false>(a.L.blk(k, tgt), a.L.ld(tgt), xs, a.b + tgt * NB, Np, S);
+    };
+
+    const int64_t kfirst = BACKWARD ? nblk - 1 : 0;
+    if ((int)(kfirst % W) == me) diag_solve_publish(kfirst);   // the first block needs no update
+
+    for (int64_t kk = 0; kk + 1 < nblk; kk++) {
+        const int64_t k = BACKWARD ? nblk - 1 - kk : kk;
+        // nearest owned target first: when it is the block next to k it gates the whole chain
+        int64_t first;
+        if (!BACKWARD) { first = k + 1 + (((me - (k + 1)) % W) + W) % W; if (first >= nblk) continue; }
+        else           { first = k - 1 - ((((k - 1) - me) % W) + W) % W; if (first < 0) continue; }
+        const bool critical = BACKWARD ? (first == k - 1) : (first == k + 1);
+        // pull the operands of the critical path into L2 BEFORE waiting for x_k
+        if (PF) {
+            if (!BACKWARD) prefetch_block_l2(a.L.blk(first, k), a.L.ld(k));
+            else prefetch_block_l2(a.L.blk(k, first), a.L.ld(first));
+            if (critical) prefetch_block_l2(a.invL + first * (int64_t)NB * NB, NB);
+        }
+        if (threadIdx.x == 0) spin_until(a.ready + k, 1u);
+        __syncthreads();
+        load_x(k);
+        if (!BACKWARD) {
+            for (int64_t i = first; i < nblk; i += W) {
+                update(i, k);
+                if (i == k + 1) { diag_solve_publish(i); load_x(k); }   // b_{k+1} just became final
+            }
+        } else {
+            for (int64_t j = first; j >= 0; j -= W) {
+                update(j, k);
+                if (j == k - 1) { diag_solve_publish(j); load_x(k); }
             }
         }
     }
@@ -457,13 +533,19 @@ __global__ void add_diag_kernel(Packed L, const double* __restrict__ d, int64_t 
 // whole forward (backward = true: transposed) sweep b <- L^{-1} b / L^{-T} b in ONE launch;
 // flags: 2*nblk unsigned scratch (zeroed here)
 void launch_sweep(Packed L, const double* invL, double* b, int S, bool backward, unsigned* flags, int num_sms,
-                  cudaStream_t s) {
+                  cudaStream_t s, int variant) {
     const int64_t nblk = L.nblk();
     cudaMemsetAsync(flags, 0, 2 * nblk * sizeof(unsigned), s);
     SweepArgs a{L, invL, b, S, flags, flags + nblk};
-    int grid = nblk < 4 ? 1 : (int)(nblk + 1 < num_sms ? nblk + 1 : num_sms);
-    if (backward) sweep_kernel<true><<<grid, 256, 0, s>>>(a);
-    else sweep_kernel<false><<<grid, 256, 0, s>>>(a);
+    if (variant == 1 || variant == 3) {   // B: owner does the diagonal solve (1: with L2 prefetch)
+        int grid = (int)(nblk < num_sms ? nblk : num_sms);
+        if (variant == 1) { if (backward) sweep_kernel_b<true, true><<<grid, 256, 0, s>>>(a); else sweep_kernel_b<false, true><<<grid, 256, 0, s>>>(a); }
+        else              { if (backward) sweep_kernel_b<true, false><<<grid, 256, 0, s>>>(a); else sweep_kernel_b<false, false><<<grid, 256, 0, s>>>(a); }
+    } else {                              // A: dedicated diagonal-solve CTA (2: with L2 prefetch)
+        int grid = nblk < 4 ? 1 : (int)(nblk + 1 < num_sms ? nblk + 1 : num_sms);
+        if (variant == 2) { if (backward) sweep_kernel_a<true, true><<<grid, 256, 0, s>>>(a); else sweep_kernel_a<false, true><<<grid, 256, 0, s>>>(a); }
+        else              { if (backward) sweep_kernel_a<true, false><<<grid, 256, 0, s>>>(a); else sweep_kernel_a<false, false><<<grid, 256, 0, s>>>(a); }
+    }
     g_launch_count++;
 }
 

@@ -424,6 +424,35 @@ function cov(fp::B200ApproxPosteriorGP, xs::AbstractVector)
     K
 end
 
+# ---- gradients of logpdf (what Zygote + ChainRules deliver in the reference, cross.jl:8-22) -----------
+# returns (g_terms, g_noise_diag): g_terms[2t-1] = d/d coeff_t, g_terms[2t] = d/d log(input scale_t) per
+# term of the symmetric spec, g_noise_diag[i] = d/d Sigma_y[i,i]; the caller applies its chain rule.
+function logpdf_grad(fx::B200Finite, y::AbstractVector{<:Real})
+    fp = posterior(fx, y); install_alpha!(fp)
+    ps, vs = components(fx.f, fx.x)
+    spec, keep = build_spec(ps, vs, ps, vs; which=:sym)
+    g = zeros(2 * max(1, Int(spec.nterms))); qd = zeros(npoints(fx.x))
+    GC.@preserve keep g qd check(ccall((:sb_logpdf_grad, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ref{SbCovSpec}, Ptr{Float64}, Ptr{Cvoid}), ctx().h, fp.F.h, spec, g, qd))
+    g, qd
+end
+
+# ---- factor checkpoint / resume --------------------------------------------------------------------------
+function save_factor(F::Factor)
+    n = Ref{Int64}(0)
+    check(ccall((:sb_factor_export_size, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Int64}), ctx().h, F.h, n))
+    blob = Vector{UInt8}(undef, n[])
+    GC.@preserve blob check(ccall((:sb_factor_export, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64),
+                                  ctx().h, F.h, blob, n[]))
+    blob
+end
+function load_factor(blob::Vector{UInt8}, n::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve blob check(ccall((:sb_factor_import, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}),
+                                  ctx().h, blob, length(blob), h))
+    F = Factor(h[], n, nothing); finalizer(destroy!, F); F
+end
+
 # ---- timings (CUDA-event phase timers of the library) ------------------------------------------------
 struct SbTimings
     assemble_ms::Float64; panel_ms::Float64; trailing_ms::Float64; solve_ms::Float64; predict_ms::Float64
@@ -440,6 +469,6 @@ end
 set_option!(key::AbstractString, value::Integer) =
     check(ccall((:sb_ctx_set_option, LIB), Int32, (Ptr{Cvoid}, Cstring, Int64), ctx().h, key, value))
 
-export b200, B200GPPP, timings, set_option!
+export b200, B200GPPP, timings, set_option!, logpdf_grad, save_factor, load_factor
 
 end # module

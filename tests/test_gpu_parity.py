@@ -11,6 +11,7 @@ from models import f3_model, mixing_model, rich_model, toy_model
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
+DEFAULT_TRAILING = 1   # library default: tcgen05 int8 Ozaki trailing update (0 = fp64 DMMA)
 
 
 def both(sb, orc, builder):
@@ -200,6 +201,36 @@ def test_vfe_elbo_and_approx_posterior(sb, orc, n, m):
     np.testing.assert_allclose(vv, orc.var(po, orc.GPPPInput("f", xs)), rtol=1e-6, atol=1e-8)
 
 
+@pytest.mark.parametrize("trailing", [0, 1])
+@pytest.mark.parametrize("n,m", [(20000, 1024), (40000, 4096)])
+def test_vfe_large_m_config4_shape(sb, orc, n, m, trailing):
+    """Config-4 geometry (pseudo-points on a unit grid in the observed process, jitter 1e-9 on K_uu,
+    x ~ U(0, M), sigma^2 = 0.1) at M = 1024 / 4096: multi-block M x M factors (8 / 32 blocks), several
+    16384-row observation chunks; elbo, dtc and the approximate posterior against the oracle, on both
+    the DMMA and the tcgen05 paths."""
+    rng = np.random.default_rng(n + m)
+    x = rng.uniform(0, m, n)
+    z = np.arange(m) + 0.5
+    xs = rng.uniform(0, m, 200)
+    y = np.sin(x) + 0.3 * rng.standard_normal(n)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    fxo, fzo = fo(orc.GPPPInput("f", x), 0.1), fo(orc.GPPPInput("f", z), 1e-9)
+    eo, do = orc.elbo(orc.VFE(fzo), fxo, y), orc.dtc(orc.VFE(fzo), fxo, y)
+    po = orc.vfe_posterior(orc.VFE(fzo), fxo, y)
+    ctx = sb.default_context()
+    ctx.set_option("trailing", trailing)
+    try:
+        fxs, fzs = fs(sb.GPPPInput("f", x), 0.1), fs(sb.GPPPInput("f", z), 1e-9)
+        ap = sb.approx_posterior(sb.VFE(fzs), fxs, y)
+        np.testing.assert_allclose(ap.elbo, eo, rtol=1e-9)
+        np.testing.assert_allclose(ap.dtc, do, rtol=1e-9)
+        mm, vv = sb.mean_and_var(ap, sb.GPPPInput("f", xs))
+        np.testing.assert_allclose(mm, orc.mean(po, orc.GPPPInput("f", xs)), rtol=1e-7, atol=1e-8)
+        np.testing.assert_allclose(vv, orc.var(po, orc.GPPPInput("f", xs)), rtol=1e-6, atol=1e-8)
+    finally:
+        ctx.set_option("trailing", DEFAULT_TRAILING)
+
+
 def test_vfe_relations(sb):
     """README.md:75-78: pseudo-points == observations => elbo == logpdf; and logpdf > elbo
     (test/gp/sparse_finite_gp.jl:40-41)."""
@@ -301,6 +332,33 @@ def test_config2_full_size_properties(sb):
     idx = np.arange(0, n, 173)
     lp = _residual_identity(sb, f, sb.GPPPInput("f", x), y, dict(idx=idx, inputs=sb.GPPPInput("f", x[idx])), 0.1)
     assert -1e6 < lp < 0
+
+
+def test_config2_full_size_tcgen05_vs_dmma(sb):
+    """BASELINE config 2 at full size (N = 65536): the two independent implementations of the O(N^3)
+    -- fp64 DMMA and tcgen05 int8 Ozaki slices -- must agree on logpdf and on the posterior mean /
+    variance at 4096 test points to the north-star tolerance (rtol 1e-10)."""
+    import bench
+    n, ns = 65536, 4096
+    x, y, xs = bench.make_inputs(n, ns)
+    f = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel())))
+    ctx = sb.default_context()
+    res = {}
+    try:
+        for mode in (0, 1):
+            ctx.set_option("trailing", mode)
+            ctx.timings(reset=True)
+            fx = f(sb.GPPPInput("f", x), bench.SIGMA2)
+            lp = sb.logpdf(fx, y)
+            m, v = sb.mean_and_var(sb.posterior(fx, y), sb.GPPPInput("f", xs))
+            res[mode] = (lp, m, v, ctx.timings()["trailing_int8_ops"])
+            del fx
+    finally:
+        ctx.set_option("trailing", DEFAULT_TRAILING)
+    assert res[0][3] == 0 and res[1][3] > 0
+    assert abs(res[0][0] - res[1][0]) <= RTOL * abs(res[0][0]), (res[0][0], res[1][0])
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=RTOL, atol=1e-11)
 
 
 def test_config3_full_size_properties(sb):
@@ -464,7 +522,7 @@ def ozaki_ctx(sb):
     try:
         yield ctx
     finally:
-        ctx.set_option("trailing", int(__import__("os").environ.get("SB_TEST_DEFAULT_TRAILING", "0")))
+        ctx.set_option("trailing", DEFAULT_TRAILING)
 
 
 @pytest.mark.parametrize("n", [2500, 4096])
@@ -489,6 +547,31 @@ def test_tcgen05_ozaki_trailing_update_parity(sb, orc, ozaki_ctx, n):
     mo, vo = orc.mean_and_var(orc.posterior(fxo, y), orc.GPPPInput("f", xs))
     np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-11)
     np.testing.assert_allclose(v, vo, rtol=RTOL, atol=1e-11)
+
+
+def test_dmma_trailing_update_parity(sb, orc):
+    """The fp64 DMMA path (SB_TRAILING=dmma / option trailing=0) stays covered now that tcgen05 is the default."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(43)
+    n = 3000
+    x, xs = rng.uniform(0, n / 32, n), rng.uniform(0, n / 32, 100)
+    y = np.sin(x) + 0.3 * rng.standard_normal(n)
+    fs, fo = sb.gppp(lambda GP: dict(f=GP(sb.SEKernel()))), orc.gppp(lambda GP: dict(f=GP(orc.SEKernel())))
+    ctx = sb.default_context()
+    ctx.set_option("trailing", 0)
+    try:
+        fxs, fxo = fs(sb.GPPPInput("f", x), 0.1), fo(orc.GPPPInput("f", x), 0.1)
+        ctx.timings(reset=True)
+        lp, lpo = sb.logpdf(fxs, y), orc.logpdf(fxo, y)
+        assert ctx.timings()["trailing_int8_ops"] == 0
+        assert abs(lp - lpo) <= RTOL * abs(lpo)
+        np.testing.assert_allclose(fxs.factor().to_dense_L(), sla.cholesky(orc.cov(fxo), lower=True), rtol=0, atol=1e-12)
+        m, v = sb.mean_and_var(sb.posterior(fxs, y), sb.GPPPInput("f", xs))
+        mo, vo = orc.mean_and_var(orc.posterior(fxo, y), orc.GPPPInput("f", xs))
+        np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-11)
+        np.testing.assert_allclose(v, vo, rtol=RTOL, atol=1e-11)
+    finally:
+        ctx.set_option("trailing", DEFAULT_TRAILING)
 
 
 def test_tcgen05_ozaki_gppp_badly_scaled_rows(sb, orc, ozaki_ctx):

@@ -144,7 +144,8 @@ def test_shim_covers_the_overridden_entry_points():
     need = {"sb_ctx_create", "sb_ctx_destroy", "sb_last_error", "sb_cov_dense", "sb_cov_diag", "sb_factor_create",
             "sb_factor_destroy", "sb_logpdf", "sb_factor_set_data", "sb_factor_alpha", "sb_factor_set_alpha",
             "sb_predict", "sb_predict_cov", "sb_predict_factor", "sb_rand", "sb_vfe_create", "sb_vfe_predict",
-            "sb_vfe_predict_cov", "sb_vfe_destroy", "sb_ctx_timings"}
+            "sb_vfe_predict_cov", "sb_vfe_destroy", "sb_ctx_timings", "sb_ctx_set_option", "sb_logpdf_grad",
+            "sb_factor_export_size", "sb_factor_export", "sb_factor_import"}
     assert need <= used, need - used
     # the methods a Stheno user calls on this path
     for sig in ["logpdf(fx::B200Finite", "posterior(fx::B200Finite", "elbo(v::AbstractGPs.VFE", "posterior(v::AbstractGPs.VFE",

@@ -140,7 +140,10 @@ int main(int argc, char** argv) {
         struct Variant { const char* name; int tma_mode; int lbo_override; int sbo_override; };
         // (round 2: all three encodings below reproduce the CPU digit products exactly on B200; the
         //  LBO field is indeed ignored for swizzled K-major operands)
-        Variant vars[] = {{"sw64 x2 stages", 0, -1, -1}, {"sw32 x5 stages", 2, -1, -1}, {"interleave default", 1, -1, -1}};
+        Variant vars[] = {{"sw64 x2 stages", 0, -1, -1}, {"sw32 x5 stages", 2, -1, -1}, {"interleave default", 1, -1, -1},
+                          {"sw64 x2, A via TMEM", 4, -1, -1}, {"sw32 x5, A via TMEM", 6, -1, -1},
+                          {"sw64 x2, paired N=128", 8, -1, -1}, {"sw32 x5, paired N=128", 10, -1, -1},
+                          {"ring: 18 A-plane slots, paired N", 16, -1, -1}};
         for (auto& v : vars) {
             CK(cudaMemcpy(pr.A2, h0.data(), tot * 8, cudaMemcpyHostToDevice));
             CK(cudaMemset(dbg, 0xff, 7 * 128 * 64 * 4));
@@ -222,7 +225,7 @@ int main(int argc, char** argv) {
         CK(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&ms, e0, e1);
         printf("[time] slice kernels %.3f ms\n", ms);
-        for (int mode = 0; mode <= 2; mode += 2) {
+        for (int mode : {0, 8, 16}) {
             OzMaps maps; OzDesc d;
             if (oz_make_maps(pr.planes, NpT, mode, &maps)) { printf("map fail\n"); continue; }
             oz_default_desc(&d, mode);
