@@ -97,7 +97,7 @@ struct sb_ctx {
     int trailing_mode = 0;   // 0: fp64 DMMA (mma.sync), 1: tcgen05 int8 Ozaki slices (ozaki.cu)
     int num_sms = 148;
     int oz_mode = SB_DEFAULT_OZ_MODE;  // SB_OZ_MODE=0|2
-    int sweep_variant = 0;      // SB_SOLVE=a|b: persistent sweep variant (solve.cu)
+    int sweep_variant = 2;      // persistent sweep variant (solve.cu): 2 = diag CTA + L2 prefetch (fastest measured)
     bool legacy_solve = false;  // SB_SOLVE=legacy: two launches per block instead of the persistent sweep
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // caching device allocator: the factor (17 GB at N=65536) and the posterior workspace are
@@ -691,7 +691,8 @@ int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
     if (om) { int m = atoi(om); if (m == 0 || m == 2 || m == 4 || m == 6 || m == 8 || m == 10 || m == 16) c->oz_mode = m; }
     const char* sv = getenv("SB_SOLVE");
     c->legacy_solve = sv && !strcmp(sv, "legacy");
-    c->sweep_variant = (sv && !strcmp(sv, "b")) ? 1 : 0;
+    if (sv && !strcmp(sv, "a")) c->sweep_variant = 0;
+    if (sv && !strcmp(sv, "b")) c->sweep_variant = 1;
     const char* tr = getenv("SB_TRAILING");   // "dmma" | "ozaki"
     c->trailing_mode = SB_DEFAULT_TRAILING;
     if (tr && !strcmp(tr, "dmma")) c->trailing_mode = 0;

@@ -366,8 +366,11 @@ __global__ void __launch_bounds__(256) sweep_kernel_b(SweepArgs a) {
     }
 }
 
+// Deterministic reductions (round 2): per-block partial sums land in a scratch buffer and are added in
+// a fixed order by a second tiny kernel -- no fp64 atomics, so logpdf / mean / var are bit-reproducible
+// from run to run (and an imported factor reproduces the original bit for bit).
 __global__ void __launch_bounds__(256)
-colsumsq_kernel(const double* __restrict__ v, int64_t n, int64_t ld, double* __restrict__ out) {
+colsumsq_kernel(const double* __restrict__ v, int64_t n, int64_t ld, double* __restrict__ partial) {
     const double* p = v + (int64_t)blockIdx.y * ld;
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
@@ -380,11 +383,21 @@ colsumsq_kernel(const double* __restrict__ v, int64_t n, int64_t ld, double* __r
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; w++) t += red[w];
-        atomicAdd(&out[blockIdx.y], t);
+        partial[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
 }
 
-// y[M] += W[M x n] * a[n], columns split across blockIdx.y
+// out[j] = sum_i partial[j * m + i]  in index order (one thread per output)
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int64_t m, int64_t nout, double* __restrict__ out,
+                                    int accumulate) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nout) return;
+    double t = 0.0;
+    for (int64_t i = 0; i < m; i++) t += partial[j * m + i];
+    out[j] = accumulate ? out[j] + t : t;
+}
+
+// partial[cy * M + r] = sum over the 512 columns of chunk cy of W[r, c] a[c]
 constexpr int GN_COLS = 512;
 __global__ void __launch_bounds__(256)
 gemv_n_kernel(const double* __restrict__ W, int64_t ld, int64_t M, int64_t n,
@@ -400,7 +413,16 @@ gemv_n_kernel(const double* __restrict__ W, int64_t ld, int64_t M, int64_t n,
     double acc = 0.0;
 #pragma unroll 8
     for (int c = 0; c < nc; c++) acc = fma(p[(int64_t)c * ld], as[c], acc);
-    atomicAdd(&y[r], acc);
+    y[(int64_t)blockIdx.y * M + r] = acc;   // y = partial buffer [chunks][M]
+}
+
+// y[r] = sum over chunks (fixed order)
+__global__ void sum_chunks_kernel(const double* __restrict__ partial, int64_t M, int64_t chunks, double* __restrict__ y) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    double t = 0.0;
+    for (int64_t c = 0; c < chunks; c++) t += partial[c * M + r];
+    y[r] = t;
 }
 
 __global__ void __launch_bounds__(256)
@@ -408,14 +430,13 @@ rowsumsq_acc_kernel(const double* __restrict__ X, int64_t ld, int64_t M, int64_t
                     double* __restrict__ acc_out) {
     int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= M) return;
-    int64_t c0 = (int64_t)blockIdx.y * 32;
     double acc = 0.0;
 #pragma unroll 8
-    for (int64_t c = c0; c < c0 + 32 && c < ncols; c++) {
+    for (int64_t c = 0; c < ncols; c++) {
         double v = X[c * ld + r];
         acc = fma(v, v, acc);
     }
-    atomicAdd(&acc_out[r], acc);
+    acc_out[r] += acc;   // one thread per row, calls are stream-ordered: deterministic
 }
 
 __global__ void axpy1_kernel(double* y, const double* x, int64_t n) {
@@ -435,25 +456,27 @@ __global__ void unpack_lower_kernel(Packed L, int64_t N, double* __restrict__ ou
     out[c * N + r] = (r >= c) ? *L.at(r, c) : 0.0;
 }
 
-// out[r] += sum_c L[r, c] z[c] over one NB x NB block (I, J), J <= I
+// out[rows of block I, sample s] = sum_{J <= I} L[I, J] z_J: one CTA per (block row, sample), the J loop is
+// sequential inside the CTA (deterministic; rand(rng, fx) reproduces bit for bit)
 __global__ void __launch_bounds__(NB)
 trmv_lower_kernel(Packed L, int64_t N, const double* __restrict__ z, double* __restrict__ out,
                   int S) {
-    int64_t I = blockIdx.x, J = blockIdx.y;
-    if (J > I) return;
+    const int64_t I = blockIdx.x;
+    const int s = blockIdx.y;
     __shared__ double zs[NB];
     const int i = threadIdx.x;
-    const double* blk = L.blk(I, J);
-    const int64_t ld = L.ld(J);
-    for (int s = 0; s < S; s++) {
+    double acc = 0.0;
+    for (int64_t J = 0; J <= I; J++) {
         __syncthreads();
         zs[i] = z[(int64_t)s * L.Np + J * NB + i];
         __syncthreads();
-        int cmax = (I == J) ? i + 1 : NB;
-        double acc = 0.0;
+        const double* blk = L.blk(I, J);
+        const int64_t ld = L.ld(J);
+        const int cmax = (I == J) ? i + 1 : NB;
+#pragma unroll 8
         for (int c = 0; c < cmax; c++) acc = fma(blk[(int64_t)c * ld + i], zs[c], acc);
-        atomicAdd(&out[(int64_t)s * L.Np + I * NB + i], acc);
     }
+    out[(int64_t)s * L.Np + I * NB + i] = acc;
 }
 
 // W[r, c] *= s[r]
@@ -613,26 +636,43 @@ void launch_gemvT_below(Packed L, int64_t k, double* b, int S, cudaStream_t s) {
     g_launch_count++;
 }
 
+// scratch for the two-stage reductions (grown on demand, one per thread / context)
+static thread_local double* g_red_scratch = nullptr;
+static thread_local size_t g_red_scratch_elems = 0;
+static double* red_scratch(size_t elems) {
+    if (elems > g_red_scratch_elems) {
+        if (g_red_scratch) cudaFree(g_red_scratch);
+        g_red_scratch = nullptr;
+        if (cudaMalloc(&g_red_scratch, elems * sizeof(double)) != cudaSuccess) { g_red_scratch_elems = 0; return nullptr; }
+        g_red_scratch_elems = elems;
+    }
+    return g_red_scratch;
+}
+
 void launch_colsumsq(const double* v, int64_t n, int64_t ld, int S, double* out, cudaStream_t s) {
-    cudaMemsetAsync(out, 0, sizeof(double) * S, s);
     int64_t gx = (n + 255) / 256;
-    if (gx > 1024) gx = 1024;
-    colsumsq_kernel<<<dim3((unsigned)gx, S), 256, 0, s>>>(v, n, ld, out);
-    g_launch_count++;
+    if (gx > 256) gx = 256;
+    double* part = red_scratch((size_t)gx * S);
+    if (!part) return;
+    colsumsq_kernel<<<dim3((unsigned)gx, S), 256, 0, s>>>(v, n, ld, part);
+    sum_partials_kernel<<<(unsigned)((S + 63) / 64), 64, 0, s>>>(part, gx, S, out, 0);
+    g_launch_count += 2;
 }
 
 void launch_gemv_n(const double* W, int64_t ld, int64_t M, int64_t n, const double* a, double* y,
                    cudaStream_t s) {
-    cudaMemsetAsync(y, 0, sizeof(double) * M, s);
-    dim3 grid((unsigned)((M + 255) / 256), (unsigned)((n + GN_COLS - 1) / GN_COLS));
-    gemv_n_kernel<<<grid, 256, 0, s>>>(W, ld, M, n, a, y);
-    g_launch_count++;
+    const int64_t chunks = (n + GN_COLS - 1) / GN_COLS;
+    double* part = red_scratch((size_t)chunks * M);
+    if (!part) return;
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)chunks);
+    gemv_n_kernel<<<grid, 256, 0, s>>>(W, ld, M, n, a, part);
+    sum_chunks_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(part, M, chunks, y);
+    g_launch_count += 2;
 }
 
 void launch_rowsumsq_acc(const double* X, int64_t ld, int64_t M, int64_t ncols, double* acc,
                          cudaStream_t s) {
-    dim3 grid((unsigned)((M + 255) / 256), (unsigned)((ncols + 31) / 32));
-    rowsumsq_acc_kernel<<<grid, 256, 0, s>>>(X, ld, M, ncols, acc);
+    rowsumsq_acc_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(X, ld, M, ncols, acc);
     g_launch_count++;
 }
 
@@ -655,8 +695,7 @@ void launch_unpack_lower(Packed L, int64_t N, double* out, cudaStream_t s) {
 }
 
 void launch_trmv_lower(Packed L, int64_t N, const double* z, double* out, int S, cudaStream_t s) {
-    cudaMemsetAsync(out, 0, sizeof(double) * L.Np * S, s);
-    dim3 grid((unsigned)L.nblk(), (unsigned)L.nblk());
+    dim3 grid((unsigned)L.nblk(), (unsigned)S);
     trmv_lower_kernel<<<grid, NB, 0, s>>>(L, N, z, out, S);
     g_launch_count++;
 }

@@ -84,10 +84,10 @@ __global__ void k_mma16(double* out, int iters) {
 template <typename F>
 double time_ms(F launch) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    launch(); CK(cudaDeviceSynchronize());
+    launch(); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());   // a failed launch (too many registers x 1024 threads) must not be timed
     float best = 1e30f;
     for (int r = 0; r < 3; r++) {
-        CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventRecord(e0)); launch(); CK(cudaGetLastError()); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
     }
     return best;
