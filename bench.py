@@ -409,7 +409,7 @@ def gpu_main(args):
     roof_asm = {"bound": "hbm", "kernel": "assemble_kernel<packed>", "achieved": asm_bytes / (tm["assemble_ms"] / args.steps * 1e-3) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s"}
     roof_asm["frac"] = roof_asm["achieved"] / hbm_peak
-    phases = {k: tm[k] / args.steps for k in ("assemble_ms", "panel_ms", "trailing_ms", "comm_ms", "solve_ms", "predict_ms")}
+    phases = {k: tm[k] / args.steps for k in ("assemble_ms", "panel_ms", "trailing_ms", "comm_ms", "solve_ms", "predict_ms", "panel_chain_ms")}
 
     cb = None
     if args.gpus == 1 and not args.no_cpu:

@@ -130,6 +130,7 @@ typedef struct {
     int64_t trailing_launches;
     int64_t kernel_launches; /* all kernels launched by this library since last reset */
     double trailing_int8_ops; /* int8 tensor-core ops (2 * MACs) issued by the tcgen05 trailing kernel; 0 on the DMMA path */
+    double panel_chain_ms;    /* total duration of the look-ahead panel phases on the second stream (mostly hidden) */
 } sb_timings;
 
 typedef struct sb_ctx sb_ctx;

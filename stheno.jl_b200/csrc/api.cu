@@ -381,6 +381,29 @@ static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, si
 // serial potrf/TRSM/broadcast chain leaves the critical path.  Two sets of tiled panel buffers.
 constexpr int LOOKAHEAD_SMS = 8;
 
+// How many SMs T^B leaves to the concurrent panel phase.  Round-2 measurement (4 GPUs): with a fixed 8
+// SMs the panel-phase GEMMs (catch-up SYRK, TRSM-as-GEMM: up to ~2000 DMMA half-tiles per outer step)
+// crawl on 16 CTA slots and the panel chain, not the trailing update, sets the pace of the second half
+// of the factorisation (160 ms of exposed waiting in a 446 ms factorisation).  Pick the reservation that
+// balances  T^B * S/(S-r)  against  serial chain + panel GEMM work / r.
+static int pick_lookahead_sms(int num_sms, double tilesB_half, bool oz, int nq_next, int64_t rows_next, int world) {
+    const double t_tile_us = oz ? 14.5 : 2 * 16.5;                 // per half-tile per SM (measured)
+    const double serial_us = nq_next * (world > 1 ? 230.0 : 150.0); // potrf + (broadcast latency)
+    // DMMA half-tiles of the next panel phase: TRSM (nq panels) + catch-up (0 + 1 + 2 + 3 segments)
+    const double gemm_tiles = (double)nq_next * (rows_next / 64.0) * (1.0 + 0.5 * (nq_next - 1) * 0.5);
+    const int cand[] = {8, 12, 16, 24, 32, 48, 64};
+    int best = LOOKAHEAD_SMS;
+    double best_t = 1e30;
+    for (int r : cand) {
+        if (r >= num_sms / 2) break;
+        const double tB = tilesB_half * t_tile_us / (num_sms - r);
+        const double tP = serial_us + gemm_tiles * 8.4 / (2.0 * r);
+        const double t = tB > tP ? tB : tP;
+        if (t < best_t - 1e-9) { best_t = t; best = r; }
+    }
+    return best;
+}
+
 struct CommEv { cudaEvent_t a, b; };
 
 static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* const* Pw, const double* const* Pt,
@@ -413,7 +436,7 @@ static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* 
 
 static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) {
     const int64_t nblk = f->L.nblk(), Np = f->Np;
-    std::vector<CommEv> comm_ev;
+    std::vector<CommEv> comm_ev, chain_ev;
     cudaStream_t s1 = c->stream, s2 = c->stream2;
     const int64_t nsteps = (nblk + OUTER_BLOCKS - 1) / OUTER_BLOCKS;
     double* Pw[2][OUTER_BLOCKS];
@@ -465,13 +488,22 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
             if (s + 1 < nsteps) {
                 const int nq1 = (int)(nblk - jt < OUTER_BLOCKS ? nblk - jt : OUTER_BLOCKS);
                 SB_CUDA(cudaStreamWaitEvent(s2, ev_a[s], 0));
+                CommEv ch{nullptr, nullptr};
+                if (c->fine_timing) { ch.a = c->next_event(); ch.b = c->next_event(); SB_CUDA(cudaEventRecord(ch.a, s2)); }
                 SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2, &comm_ev));
                 if (f->oz)  // digit planes of the trailing rows of the panels just factored (block rows >= jt + nq1)
                     launch_oz_slice(oz_src_tiled(Pt[set ^ 1], nq1), nq1 - 1, nblk - (jt + nq1), (jt + 1) * (int64_t)NB, Np,
                                     f->oz_scale[set ^ 1], f->oz_expo[set ^ 1], f->oz_planes[set ^ 1], s2);
                 SB_CUDA(cudaEventRecord(ev_p[s + 1], s2));
+                if (ch.a) { SB_CUDA(cudaEventRecord(ch.b, s2)); chain_ev.push_back(ch); }
             }
-            if (jA < nblk) SB_TRY(trailing(jA, nblk, LOOKAHEAD_SMS));                      // T^B
+            if (jA < nblk) {                                                                // T^B
+                const double tilesB = 2.0 * (double)syrk_packed_tiles(nblk, k0, jA, nblk, rank, world);
+                const int nq1 = (int)(nblk - jt < OUTER_BLOCKS ? nblk - jt : OUTER_BLOCKS);
+                const int reserve = (s + 1 < nsteps)
+                    ? pick_lookahead_sms(c->num_sms, tilesB, f->oz, nq1, Np - (jt + 1) * NB, world) : 0;
+                SB_TRY(trailing(jA, nblk, reserve));
+            }
             int64_t tiles = syrk_packed_tiles(nblk, k0, jt, nblk, rank, world);
             if (tiles > 0) { flops += (double)tiles * 2.0 * NB * NB * ((double)nq * NB); nlaunch++; }
         }
@@ -497,6 +529,11 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
             float cm = 0;
             cudaEventElapsedTime(&cm, ce.a, ce.b);
             c->tm.comm_ms += cm;
+        }
+        for (auto& ce : chain_ev) {   // total duration of the look-ahead panel phases (stream 2)
+            float cm = 0;
+            cudaEventElapsedTime(&cm, ce.a, ce.b);
+            c->tm.panel_chain_ms += cm;
         }
     }
     c->tm.trailing_flops += flops;

@@ -394,7 +394,8 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                 const uint32_t sA = base + st * OZ_STAGE_BYTES, sB = sA + OZ_A_STAGE;
                 const uint32_t a0 = (sA >> 4) | (D_LBO_A << 16), b0 = (sB >> 4) | (D_LBO_B << 16);
                 const uint32_t acc0 = kc > 0 ? 1u : 0u;
-                if constexpr (PAIR) {
+                constexpr bool PAIRTS = PAIR && ATMEM;
+                if constexpr (PAIR && !ATMEM) {
                     // Two digit planes of B per instruction.  Measured (round 2, tools/oz_test ablations): an
                     // M=128 N=64 K=32 int8 MMA takes ~71 clk however its operands are fed (smem or TMEM), i.e.
                     // the instruction has a ~64 clk floor and N=64 runs the tensor pipe at half rate.  The B
@@ -464,22 +465,48 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                             const uint32_t alo = a0 + (uint32_t)(p * (OZ_A_PLANE >> 4)) + (uint32_t)kk * D_KK_A;
                             if (leader) tmem_cp_128x256b(tmem + A_TMEM_COL + (uint32_t)p * 8, alo, D_HI);
                         }
+                        if constexpr (!PAIRTS) {
 #pragma unroll
-                        for (int grp = 0; grp < OZ_S; grp++) {
-                            if (kc == 0 && kk == 0) {
-                                mbar_wait(tempty0 + 8 * grp, (it & 1) ^ 1);
-                                tc_fence_after();
-                            }
-                            const uint32_t d = tmem + (uint32_t)grp * OZ_BN;
+                            for (int grp = 0; grp < OZ_S; grp++) {
+                                if (kc == 0 && kk == 0) {
+                                    mbar_wait(tempty0 + 8 * grp, (it & 1) ^ 1);
+                                    tc_fence_after();
+                                }
+                                const uint32_t d = tmem + (uint32_t)grp * OZ_BN;
 #pragma unroll
-                            for (int p = 0; p <= grp; p++) {
-                                const int q = grp - p;
-                                const uint32_t blo = b0 + (uint32_t)(q * (OZ_B_PLANE >> 4)) + (uint32_t)kk * D_KK_B;
-                                if (leader)
-                                    mma_i8_ts(d, tmem + A_TMEM_COL + (uint32_t)p * 8, blo, D_HI, idesc,
-                                              (p > 0 || kk > 0) ? 1u : acc0);
+                                for (int p = 0; p <= grp; p++) {
+                                    const int q = grp - p;
+                                    const uint32_t blo = b0 + (uint32_t)(q * (OZ_B_PLANE >> 4)) + (uint32_t)kk * D_KK_B;
+                                    if (leader)
+                                        mma_i8_ts(d, tmem + A_TMEM_COL + (uint32_t)p * 8, blo, D_HI, idesc,
+                                                  (p > 0 || kk > 0) ? 1u : acc0);
+                                }
+                                if (kc == g.kchunks - 1 && kk == OZ_KC / 32 - 1 && leader) tc_commit(tfull0 + 8 * grp);
                             }
-                            if (kc == g.kchunks - 1 && kk == OZ_KC / 32 - 1 && leader) tc_commit(tfull0 + 8 * grp);
+                        } else {
+                            // A from TMEM AND two B planes per instruction (N = 128)
+                            constexpr uint32_t idesc128 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * OZ_BN >> 3) << 17) |
+                                                          ((uint32_t)(OZ_BM >> 4) << 24);
+#pragma unroll
+                            for (int p = 0; p < OZ_S; p++) {
+#pragma unroll
+                                for (int q = 0; q < OZ_S - p; q += 2) {
+                                    const bool two = (q + 1 < OZ_S - p);
+                                    if (kc == 0 && kk == 0 && p == 0) {
+                                        mbar_wait(tempty0 + 8 * q, (it & 1) ^ 1);
+                                        if (two) mbar_wait(tempty0 + 8 * (q + 1), (it & 1) ^ 1);
+                                        tc_fence_after();
+                                    }
+                                    const uint32_t blo = b0 + (uint32_t)(q * (OZ_B_PLANE >> 4)) + (uint32_t)kk * D_KK_B;
+                                    if (leader)
+                                        mma_i8_ts(tmem + (uint32_t)(p + q) * OZ_BN, tmem + A_TMEM_COL + (uint32_t)p * 8, blo, D_HI,
+                                                  two ? idesc128 : idesc, (p > 0 || kk > 0) ? 1u : acc0);
+                                }
+                            }
+                            if (kc == g.kchunks - 1 && kk == OZ_KC / 32 - 1 && leader) {
+#pragma unroll
+                                for (int grp = 0; grp < OZ_S; grp++) tc_commit(tfull0 + 8 * grp);
+                            }
                         }
                     }
                 }
@@ -706,6 +733,7 @@ int g_oz_sms = 0;
         if ((mode) == 2) { CALL(32, 5, 2, false, false); } else if ((mode) == 1) { CALL(64, 2, 1, false, false); }       \
         else if ((mode) == 4) { CALL(64, 2, 0, true, false); } else if ((mode) == 6) { CALL(32, 5, 2, true, false); }     \
         else if ((mode) == 8) { CALL(64, 2, 0, false, true); } else if ((mode) == 10) { CALL(32, 5, 2, false, true); }    \
+        else if ((mode) == 12) { CALL(64, 2, 0, true, true); }                                                            \
         else { CALL(64, 2, 0, false, false); }                                                                            \
     } while (0)
 
@@ -722,7 +750,7 @@ int oz_init() {
                                  (int)OzCfg<KC, ST>::SMEM) != cudaSuccess) return -2
         OZ_ATTR(64, 2, 0, false, false); OZ_ATTR(64, 2, 1, false, false); OZ_ATTR(32, 5, 2, false, false);
         OZ_ATTR(64, 2, 0, true, false); OZ_ATTR(32, 5, 2, true, false);
-        OZ_ATTR(64, 2, 0, false, true); OZ_ATTR(32, 5, 2, false, true);
+        OZ_ATTR(64, 2, 0, false, true); OZ_ATTR(32, 5, 2, false, true); OZ_ATTR(64, 2, 0, true, true);
         if (cudaFuncSetAttribute(ozaki_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM) != cudaSuccess) return -2;
 #undef OZ_ATTR
         int dev = 0;

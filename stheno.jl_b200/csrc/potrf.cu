@@ -97,7 +97,21 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
             double li[PB];
 #pragma unroll
             for (int p = 0; p < PB; p++) li[p] = s[(j0 + p) * LDS + ri];
-            for (int l = j0 + PB + lg; l <= ri; l += PT / NB) {
+            // two columns per iteration: two independent FMA chains (the 8-deep dependent chain was
+            // latency-bound: potrf_inv measured 198 us per block in round 1, all of the panel chain)
+            int l = j0 + PB + lg;
+            for (; l + PT / NB <= ri; l += 2 * (PT / NB)) {
+                const int l2 = l + PT / NB;
+                double acc = s[l * LDS + ri], acc2 = s[l2 * LDS + ri];
+#pragma unroll
+                for (int p = 0; p < PB; p++) {
+                    acc = fma(-li[p], s[(j0 + p) * LDS + l], acc);
+                    acc2 = fma(-li[p], s[(j0 + p) * LDS + l2], acc2);
+                }
+                s[l * LDS + ri] = acc;
+                s[l2 * LDS + ri] = acc2;
+            }
+            for (; l <= ri; l += PT / NB) {
                 double acc = s[l * LDS + ri];
 #pragma unroll
                 for (int p = 0; p < PB; p++) acc = fma(-li[p], s[(j0 + p) * LDS + l], acc);
@@ -169,12 +183,23 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
         if (ri >= j0 + PB) {
             const double* t0 = s + (j0 + 2 * q) * LDS;
             const double* t1 = t0 + LDS;
-#pragma unroll 4
-            for (int p = j0 + PB; p <= ri; p++) {
-                double xv = s[p * LDS + ri];
+            double y0b = 0.0, y1b = 0.0;   // four independent chains instead of two
+            int p = j0 + PB;
+#pragma unroll 2
+            for (; p + 1 <= ri; p += 2) {
+                const double xv = s[p * LDS + ri], xw = s[(p + 1) * LDS + ri];
+                y0 = fma(xv, t0[p], y0);
+                y1 = fma(xv, t1[p], y1);
+                y0b = fma(xw, t0[p + 1], y0b);
+                y1b = fma(xw, t1[p + 1], y1b);
+            }
+            if (p <= ri) {
+                const double xv = s[p * LDS + ri];
                 y0 = fma(xv, t0[p], y0);
                 y1 = fma(xv, t1[p], y1);
             }
+            y0 += y0b;
+            y1 += y1b;
             ybuf[(2 * q) * NB + ri] = y0;
             ybuf[(2 * q + 1) * NB + ri] = y1;
         }

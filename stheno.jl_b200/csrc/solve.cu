@@ -425,18 +425,24 @@ __global__ void sum_chunks_kernel(const double* __restrict__ partial, int64_t M,
     y[r] = t;
 }
 
+// acc[r] += sum_c X[r, c]^2: 4 lanes per row (32 columns each, interleaved), combined by shuffles in a
+// fixed order -- deterministic, and 4x the parallelism of one thread per row
 __global__ void __launch_bounds__(256)
 rowsumsq_acc_kernel(const double* __restrict__ X, int64_t ld, int64_t M, int64_t ncols,
                     double* __restrict__ acc_out) {
-    int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (r >= M) return;
+    const int part = threadIdx.x & 3;
+    int64_t r = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2);
     double acc = 0.0;
+    if (r < M) {
 #pragma unroll 8
-    for (int64_t c = 0; c < ncols; c++) {
-        double v = X[c * ld + r];
-        acc = fma(v, v, acc);
+        for (int64_t c = part; c < ncols; c += 4) {
+            double v = X[c * ld + r];
+            acc = fma(v, v, acc);
+        }
     }
-    acc_out[r] += acc;   // one thread per row, calls are stream-ordered: deterministic
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0 && r < M) acc_out[r] += acc;
 }
 
 __global__ void axpy1_kernel(double* y, const double* x, int64_t n) {
@@ -672,7 +678,7 @@ void launch_gemv_n(const double* W, int64_t ld, int64_t M, int64_t n, const doub
 
 void launch_rowsumsq_acc(const double* X, int64_t ld, int64_t M, int64_t ncols, double* acc,
                          cudaStream_t s) {
-    rowsumsq_acc_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(X, ld, M, ncols, acc);
+    rowsumsq_acc_kernel<<<(unsigned)((M + 63) / 64), 256, 0, s>>>(X, ld, M, ncols, acc);
     g_launch_count++;
 }
 

@@ -457,7 +457,7 @@ end
 struct SbTimings
     assemble_ms::Float64; panel_ms::Float64; trailing_ms::Float64; solve_ms::Float64; predict_ms::Float64
     comm_ms::Float64; total_ms::Float64; trailing_flops::Float64; trailing_kernel_ms::Float64
-    trailing_launches::Int64; kernel_launches::Int64; trailing_int8_ops::Float64
+    trailing_launches::Int64; kernel_launches::Int64; trailing_int8_ops::Float64; panel_chain_ms::Float64
 end
 function timings(; reset::Bool=false)
     t = Ref{SbTimings}()

@@ -44,7 +44,8 @@ class sb_timings(C.Structure):
                 ("solve_ms", C.c_double), ("predict_ms", C.c_double), ("comm_ms", C.c_double),
                 ("total_ms", C.c_double), ("trailing_flops", C.c_double),
                 ("trailing_kernel_ms", C.c_double), ("trailing_launches", C.c_int64),
-                ("kernel_launches", C.c_int64), ("trailing_int8_ops", C.c_double)]
+                ("kernel_launches", C.c_int64), ("trailing_int8_ops", C.c_double),
+                ("panel_chain_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

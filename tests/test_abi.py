@@ -44,4 +44,4 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(lib.sb_block) == 40
     assert ctypes.sizeof(lib.sb_covspec) == 64
     assert ctypes.sizeof(lib.sb_noise) == 24
-    assert ctypes.sizeof(lib.sb_timings) == 96
+    assert ctypes.sizeof(lib.sb_timings) == 104

@@ -143,7 +143,7 @@ int main(int argc, char** argv) {
         Variant vars[] = {{"sw64 x2 stages", 0, -1, -1}, {"sw32 x5 stages", 2, -1, -1}, {"interleave default", 1, -1, -1},
                           {"sw64 x2, A via TMEM", 4, -1, -1}, {"sw32 x5, A via TMEM", 6, -1, -1},
                           {"sw64 x2, paired N=128", 8, -1, -1}, {"sw32 x5, paired N=128", 10, -1, -1},
-                          {"ring: 18 A-plane slots, paired N", 16, -1, -1}};
+                          {"ring: 18 A-plane slots, paired N", 16, -1, -1}, {"sw64 x2, A via TMEM + paired N", 12, -1, -1}};
         for (auto& v : vars) {
             CK(cudaMemcpy(pr.A2, h0.data(), tot * 8, cudaMemcpyHostToDevice));
             CK(cudaMemset(dbg, 0xff, 7 * 128 * 64 * 4));
@@ -225,7 +225,7 @@ int main(int argc, char** argv) {
         CK(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&ms, e0, e1);
         printf("[time] slice kernels %.3f ms\n", ms);
-        for (int mode : {0, 8, 16}) {
+        for (int mode : {8, 12, 16}) {
             OzMaps maps; OzDesc d;
             if (oz_make_maps(pr.planes, NpT, mode, &maps)) { printf("map fail\n"); continue; }
             oz_default_desc(&d, mode);
