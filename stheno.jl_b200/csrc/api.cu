@@ -100,6 +100,15 @@ struct sb_ctx {
     int sweep_variant = 2;      // persistent sweep variant (solve.cu): 2 = diag CTA + L2 prefetch (fastest measured)
     bool legacy_solve = false;  // SB_SOLVE=legacy: two launches per block instead of the persistent sweep
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // peer-to-peer panel exchange over NVLink (multi-GPU, see "P2P panel exchange" below)
+    struct P2PState {
+        int state = 0;            // 0: not tried, 1: on, -1: unavailable (NCCL broadcast is used)
+        char* arena = nullptr;    // counters | head slots | panel slots; IPC-exported to every peer
+        size_t bytes = 0;
+        char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        uint32_t pub[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // panels published so far by each owner (same on all ranks)
+        void* xch = nullptr;      // handle-exchange staging
+    } p2p;
     // caching device allocator: the factor (17 GB at N=65536) and the posterior workspace are
     // re-used across calls instead of paying cudaMalloc/cudaFree (both device-synchronising)
     struct PoolBlock { size_t bytes; void* p; };
@@ -177,6 +186,15 @@ struct sb_factor {
     OzDesc oz_desc;
     int oz_mode = 0;   // TMA / pipeline variant of the tcgen05 kernel (ozaki.cu: 0 = SW64 x 2 stages, 2 = SW32 x 5 stages)
     size_t bytes_oz_planes = 0;
+    // wide panel phase (tcgen05 path, see wide_panel_phase): dense scratch of the step's 512 x 512 diagonal block
+    // stacked over an identity (input and result copies), inv(L_512) and its digit planes
+    bool wide = false;
+    double* wide_D = nullptr;        // [2][1024 x 512], ld 1024
+    double* wide_W = nullptr;        // 512 x 512, column-major
+    signed char* wide_wp = nullptr;  // digit planes of wide_W  [7][512][512]
+    double* wide_wscale = nullptr;
+    int* wide_wexpo = nullptr;
+    OzMaps wide_wmaps;
 };
 
 namespace {
@@ -358,6 +376,219 @@ struct CholEv { cudaEvent_t e[4]; };
 // One grouped broadcast per panel: inverse of the diagonal block, the diagonal block itself, its
 // logdet share and the tiled sub-diagonal panel.  Non-owners drop L_kk into their packed matrix, so
 // after the sweep every rank holds the complete factor without any extra collective.
+// ---------------------------------------------------------------------------------------------
+// P2P panel exchange.  Round-2 measurement (2 and 4 GPUs): the 512 NCCL panel broadcasts of a
+// factorisation cost 0.6-1.2 ms each next to the trailing update, because an NCCL broadcast is a
+// kernel on BOTH sides: the receivers' copies spin on SMs until the owner has factored the panel and
+// the trailing update has to give those SMs up (or the broadcast starves).  The panels are moved
+// by the copy engines instead, with no SM on the receiving side waiting for data:
+//   * every rank has one "arena" (cudaMalloc, IPC-mapped by all peers): 64 ready counters + 64 ack
+//     counters + an error word | 8 head slots (inv(L_kk), L_kk, logdet) | 8 panel slots (2 look-ahead
+//     sets x OUTER_BLOCKS tiled panels; these ARE the panel buffers the local kernels read and write);
+//   * the owner of panel k factors it into its own slot k % 8, packs the head, and bumps ready[owner]
+//     in every peer's arena (st.release.sys over NVLink);
+//   * a receiver waits on its LOCAL counter (one thread), pulls the head with a small kernel (peer
+//     loads) and the slab with cudaMemcpyAsync from the owner's mapped slot into its own slot (copy
+//     engine, NVLink read), then bumps ack[me] in the owner's arena;
+//   * before a rank overwrites slot k % 8 that last held a panel it OWNED (panel k - 8), it waits until
+//     every peer has acknowledged that panel (flow control; almost always already true).
+// Counters are absolute (never reset while the arena lives), compared wrap-safe.  A waiter gives up
+// after 20 s and raises the arena's error word, which fails the factorisation instead of hanging.
+// ---------------------------------------------------------------------------------------------
+constexpr int P2P_SLOTS = 2 * OUTER_BLOCKS;
+constexpr int64_t P2P_HEAD_ELEMS = 2 * (int64_t)NB * NB + 32;
+constexpr size_t P2P_CTR_BYTES = 4096;
+constexpr size_t P2P_HEAD_OFF = P2P_CTR_BYTES;
+constexpr size_t P2P_PANEL_OFF = P2P_HEAD_OFF + (size_t)P2P_SLOTS * P2P_HEAD_ELEMS * sizeof(double);
+constexpr int P2P_READY = 0, P2P_ACK = 64, P2P_ERR = 128;
+static_assert(P2P_PANEL_OFF % 1024 == 0, "panel slots must stay 1 KB aligned");
+struct P2PPeers { char* base[8]; };
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// thread i < count waits until ctr[first + i] has reached `target` (thread `skip` does not wait)
+__global__ void p2p_wait_kernel(const uint32_t* ctr, int first, int count, int skip, uint32_t target, uint32_t* err) {
+    const int i = threadIdx.x;
+    if (i >= count || i == skip) return;
+    const uint32_t* p = ctr + first + i;
+    const unsigned long long t0 = p2p_now_ns();
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys_u32(p) - target) < 0) {
+        if (++spins > 256) __nanosleep(50);
+        if ((spins & 4095u) == 0 && p2p_now_ns() - t0 > 20000000000ull) { atomicExch(err, 1u); return; }
+    }
+}
+
+// thread r writes `value` to counter `index` in the arena of peer r (all peers, or only `only`)
+__global__ void p2p_signal_kernel(P2PPeers peers, int world, int me, int index, uint32_t value, int only) {
+    const int r = threadIdx.x;
+    if (r >= world || r == me || (only >= 0 && r != only)) return;
+    __threadfence_system();
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(peers.base[r]) + index, value);
+}
+
+__global__ void p2p_pack_head_kernel(const double* __restrict__ invL, const double* __restrict__ ldiag,
+                                     const double* __restrict__ logdet, double* __restrict__ head) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NB * NB) { head[i] = invL[i]; head[NB * NB + i] = ldiag[i]; }
+    if (i == 0) head[2 * NB * NB] = logdet[0];
+}
+
+// reads the owner's head slot over NVLink (volatile loads: never served from a stale line) and
+// scatters it: inv(L_kk), the contiguous copy of L_kk, L_kk inside the packed factor, logdet term
+__global__ void p2p_pull_head_kernel(const double* head, double* __restrict__ invL, double* __restrict__ ldiag,
+                                     double* __restrict__ Lkk, int64_t ldL, double* __restrict__ logdet) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NB * NB) {
+        invL[i] = __ldcv(head + i);
+        const double v = __ldcv(head + NB * NB + i);
+        ldiag[i] = v;
+        Lkk[(int64_t)(i / NB) * ldL + (i % NB)] = v;
+    }
+    if (i == 0) logdet[0] = __ldcv(head + 2 * NB * NB);
+}
+
+static int32_t nccl_barrier(sb_ctx* c, void* scratch4) {
+    SB_NCCL(nccl_dl::AllReduce(scratch4, scratch4, 1, ncclInt, ncclMin, c->comm, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+static void p2p_close(sb_ctx* c) {
+    auto& P = c->p2p;
+    for (int r = 0; r < 8; r++) {
+        if (P.peer[r] && r != c->rank) cudaIpcCloseMemHandle(P.peer[r]);
+        P.peer[r] = nullptr;
+    }
+    if (P.arena) cudaFree(P.arena);
+    P.arena = nullptr;
+    P.bytes = 0;
+}
+
+// Collective: make sure every rank has an arena with panel slots for order-Np factors, mapped by all.
+// Falls back (state = -1, once, on every rank together) when CUDA IPC is not available.
+static int32_t p2p_ensure(sb_ctx* c, int64_t Np) {
+    auto& P = c->p2p;
+    if (P.state == 0) {
+        const char* e = getenv("SB_P2P");
+        if ((e && e[0] == '0') || c->world > 8) P.state = -1;
+    }
+    if (P.state < 0) return SB_OK;
+    const size_t need = P2P_PANEL_OFF + (size_t)P2P_SLOTS * tiled_panel_elems(Np) * sizeof(double);
+    if (P.state == 1 && P.bytes >= need) return SB_OK;
+    const int world = c->world, rank = c->rank;
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream2));
+    if (!P.xch) SB_CUDA(cudaMalloc(&P.xch, 8 * sizeof(cudaIpcMemHandle_t) + 64));
+    int* flag_dev = reinterpret_cast<int*>(static_cast<char*>(P.xch) + 8 * sizeof(cudaIpcMemHandle_t));
+    int one = 1;
+    SB_CUDA(cudaMemcpy(flag_dev, &one, sizeof(int), cudaMemcpyHostToDevice));
+    if (P.arena) {                       // growing: nobody may still be pulling from the old arena
+        SB_TRY(nccl_barrier(c, flag_dev));
+        p2p_close(c);
+    }
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc((void**)&P.arena, need) != cudaSuccess) { cudaGetLastError(); P.arena = nullptr; ok = 0; }
+    if (ok && cudaMemset(P.arena, 0, P2P_PANEL_OFF) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, P.arena) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    SB_CUDA(cudaMemcpy(static_cast<char*>(P.xch) + rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(flag_dev, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    SB_NCCL(nccl_dl::AllGather(static_cast<char*>(P.xch) + rank * sizeof(mine), P.xch, sizeof(mine), ncclChar, c->comm, c->stream));
+    SB_TRY(nccl_barrier(c, flag_dev));   // min over ranks of ok
+    SB_CUDA(cudaMemcpy(&ok, flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ok) {
+        cudaIpcMemHandle_t all[8];
+        SB_CUDA(cudaMemcpy(all, P.xch, world * sizeof(mine), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < world && ok; r++) {
+            if (r == rank) { P.peer[r] = P.arena; continue; }
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            P.peer[r] = static_cast<char*>(q);
+        }
+        SB_CUDA(cudaMemcpy(flag_dev, &ok, sizeof(int), cudaMemcpyHostToDevice));
+        SB_TRY(nccl_barrier(c, flag_dev));
+        SB_CUDA(cudaMemcpy(&ok, flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (!ok) {
+        p2p_close(c);
+        P.state = -1;
+        if (rank == 0) fprintf(stderr, "[stheno_b200] CUDA IPC peer mapping unavailable: panels go through ncclBroadcast\n");
+        return SB_OK;
+    }
+    P.bytes = need;
+    P.state = 1;
+    for (int r = 0; r < 8; r++) P.pub[r] = 0;
+    return SB_OK;
+}
+
+struct P2PRun {                 // one factorisation's view of the arena
+    bool on = false;
+    P2PPeers peers{};
+    int64_t slot_elems = 0;     // doubles per panel slot
+    std::vector<uint32_t> ord;  // ord[k]: absolute ordinal (1-based) of panel k among its owner's panels
+    uint32_t guarded = 0;       // acks up to this ordinal of MY panels have already been waited for on the panel stream
+    uint32_t* ctr(sb_ctx* c) const { return reinterpret_cast<uint32_t*>(c->p2p.arena); }
+    double* head(char* base, int64_t k) const {
+        return reinterpret_cast<double*>(base + P2P_HEAD_OFF) + (k % P2P_SLOTS) * P2P_HEAD_ELEMS;
+    }
+    double* slot(char* base, int s) const { return reinterpret_cast<double*>(base + P2P_PANEL_OFF) + (int64_t)s * slot_elems; }
+};
+
+// Before anything is written into slot k % 8 (TRSM output, pulled slab, packed head): the last panel this
+// rank OWNED in that slot (k - 8m) must have been pulled by every peer.  Acks are monotone per owner, so
+// one wait per new high-water mark is enough.
+static int32_t p2p_slot_guard(sb_ctx* c, P2PRun& R, int64_t k, cudaStream_t st) {
+    for (int64_t kp = k - P2P_SLOTS; kp >= 0; kp -= P2P_SLOTS) {
+        if ((int)(kp % c->world) != c->rank) continue;
+        if ((int)(R.ord[kp] - R.guarded) > 0) {
+            p2p_wait_kernel<<<1, 32, 0, st>>>(R.ctr(c), P2P_ACK, c->world, c->rank, R.ord[kp], R.ctr(c) + P2P_ERR);
+            SB_CUDA(cudaGetLastError());
+            R.guarded = R.ord[kp];
+        }
+        break;
+    }
+    return SB_OK;
+}
+
+static int32_t p2p_publish(sb_ctx* c, sb_factor* f, P2PRun& R, int64_t k, cudaStream_t st) {
+    const int64_t bo = k * (int64_t)NB * NB;
+    p2p_pack_head_kernel<<<NB * NB / 256, 256, 0, st>>>(f->invL + bo, f->ldiag + bo, f->logdet_blk + k, R.head(c->p2p.arena, k));
+    p2p_signal_kernel<<<1, 32, 0, st>>>(R.peers, c->world, c->rank, P2P_READY + c->rank, R.ord[k], -1);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+static int32_t p2p_pull(sb_ctx* c, sb_factor* f, P2PRun& R, int64_t k, int owner, int64_t slab_off, size_t slab_elems,
+                        cudaStream_t st) {
+    const int64_t bo = k * (int64_t)NB * NB;
+    p2p_wait_kernel<<<1, 32, 0, st>>>(R.ctr(c), P2P_READY + owner, 1, -1, R.ord[k], R.ctr(c) + P2P_ERR);
+    p2p_pull_head_kernel<<<NB * NB / 256, 256, 0, st>>>(R.head(c->p2p.peer[owner], k), f->invL + bo, f->ldiag + bo,
+                                                          f->L.blk(k, k), f->L.ld(k), f->logdet_blk + k);
+    SB_CUDA(cudaGetLastError());
+    if (slab_elems) {
+        const int s = (int)(k % P2P_SLOTS);
+        SB_CUDA(cudaMemcpyAsync(R.slot(c->p2p.arena, s) + slab_off, R.slot(c->p2p.peer[owner], s) + slab_off,
+                                slab_elems * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    p2p_signal_kernel<<<1, 32, 0, st>>>(R.peers, c->world, c->rank, P2P_ACK + c->rank, R.ord[k], owner);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
 static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, size_t slab_elems, int owner,
                            cudaStream_t st) {
     const int64_t bo = k * (int64_t)NB * NB;
@@ -380,24 +611,31 @@ static int32_t bcast_panel(sb_ctx* c, sb_factor* f, int64_t k, double* Pslab, si
 // LOOKAHEAD_SMS SMs).  Panel phase s+1 starts as soon as T^A_s is done and overlaps T^B_s, so the
 // serial potrf/TRSM/broadcast chain leaves the critical path.  Two sets of tiled panel buffers.
 constexpr int LOOKAHEAD_SMS = 8;
+constexpr int OZ_CHUNK_TILES = 8;   // tiles per CTA of a chunked T^B launch (multi-GPU default)
 
 // How many SMs T^B leaves to the concurrent panel phase.  Round-2 measurement (4 GPUs): with a fixed 8
 // SMs the panel-phase GEMMs (catch-up SYRK, TRSM-as-GEMM: up to ~2000 DMMA half-tiles per outer step)
 // crawl on 16 CTA slots and the panel chain, not the trailing update, sets the pace of the second half
 // of the factorisation (160 ms of exposed waiting in a 446 ms factorisation).  Pick the reservation that
 // balances  T^B * S/(S-r)  against  serial chain + panel GEMM work / r.
-static int pick_lookahead_sms(int num_sms, double tilesB_half, bool oz, int nq_next, int64_t rows_next, int world) {
+static int pick_lookahead_sms(int num_sms, double tilesB_half, bool oz, int nq_next, int64_t rows_next, int world,
+                              bool wide = false) {
     const double t_tile_us = oz ? 14.5 : 2 * 16.5;                 // per half-tile per SM (measured)
     const double serial_us = nq_next * (world > 1 ? 230.0 : 150.0); // potrf + (broadcast latency)
     // DMMA half-tiles of the next panel phase: TRSM (nq panels) + catch-up (0 + 1 + 2 + 3 segments)
     const double gemm_tiles = (double)nq_next * (rows_next / 64.0) * (1.0 + 0.5 * (nq_next - 1) * 0.5);
+    static const int forced = getenv("SB_LOOKAHEAD_SMS") ? atoi(getenv("SB_LOOKAHEAD_SMS")) : 0;
+    if (forced > 0) return forced < num_sms / 2 ? forced : num_sms / 2;
     const int cand[] = {8, 12, 16, 24, 32, 48, 64};
     int best = LOOKAHEAD_SMS;
     double best_t = 1e30;
     for (int r : cand) {
         if (r >= num_sms / 2) break;
         const double tB = tilesB_half * t_tile_us / (num_sms - r);
-        const double tP = serial_us + gemm_tiles * 8.4 / (2.0 * r);
+        // wide phase: ~0.9 ms of potrfs / small products per step, then ONE tcgen05 product of
+        // (rows / 128) x 8 half-tiles (K = 512) confined to the r free SMs
+        const double tP = wide ? 900.0 + (world > 1 ? 350.0 : 0.0) + (double)(rows_next / NB) * 8.0 * 14.5 / r
+                               : serial_us + gemm_tiles * 8.4 / (2.0 * r);
         const double t = tB > tP ? tB : tP;
         if (t < best_t - 1e-9) { best_t = t; best = r; }
     }
@@ -407,7 +645,8 @@ static int pick_lookahead_sms(int num_sms, double tilesB_half, bool oz, int nq_n
 struct CommEv { cudaEvent_t a, b; };
 
 static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* const* Pw, const double* const* Pt,
-                           int rank, int world, cudaStream_t st, std::vector<CommEv>* comm_ev) {
+                           int rank, int world, cudaStream_t st, std::vector<CommEv>* comm_ev, P2PRun* R = nullptr) {
+    const bool p2p = R && R->on;
     const int64_t Np = f->Np;
     for (int q = 0; q < nq; q++) {
         const int64_t kq = k0 + q;
@@ -417,6 +656,7 @@ static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* 
         if (owner == rank) {
             if (q > 0) launch_syrk_packed(f->L, k0, Pt, q, kq, kq + 1, rank, world, st);
             launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st, world > 1 ? f->ldiag : nullptr);
+            if (p2p) SB_TRY(p2p_slot_guard(c, *R, kq, st));
             if (mq > 0)
                 launch_trsm_tiled(f->L.blk(kq + 1, kq), f->L.ld(kq), f->invL + kq * (int64_t)NB * NB, Pq, mq, st);
         }
@@ -426,11 +666,153 @@ static int32_t panel_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, double* 
                 ce.a = c->next_event(); ce.b = c->next_event();
                 SB_CUDA(cudaEventRecord(ce.a, st));
             }
-            SB_TRY(bcast_panel(c, f, kq, Pq, mq > 0 ? (size_t)tiled_panel_elems(mq) : 0, owner, st));
+            const size_t slab = mq > 0 ? (size_t)tiled_panel_elems(mq) : 0;
+            if (!p2p) {
+                SB_TRY(bcast_panel(c, f, kq, Pq, slab, owner, st));
+            } else if (owner == rank) {
+                SB_TRY(p2p_publish(c, f, *R, kq, st));
+            } else {
+                SB_TRY(p2p_slot_guard(c, *R, kq, st));
+                SB_TRY(p2p_pull(c, f, *R, kq, owner, tiled_panel_elems((int64_t)q * NB), slab, st));
+            }
             if (ce.a) { SB_CUDA(cudaEventRecord(ce.b, st)); comm_ev->push_back(ce); }
         }
         if (mq > 0) launch_untile_panel(Pt[q], q, mq / NB, f->L.blk(kq + 1, kq), f->L.ld(kq), st);
     }
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide panel phase (tcgen05 path).  The per-panel chain  catch-up -> potrf -> TRSM -> exchange  (x 512)
+// keeps full-height DMMA products between the potrfs; measured at 2 / 4 GPUs that chain, squeezed onto the
+// SMs the trailing update leaves free, bounds the factorisation (chain 620 / 415 ms vs trailing 549 /
+// 290 ms).  Here the four block columns of an outer step are factored together:
+//   (0) multi-GPU: every owner publishes its (already updated) block column, everyone pulls the other three
+//       into its own packed matrix (copy engines, see "P2P panel exchange") -- all ranks then do the rest
+//       redundantly, so nothing but the raw columns crosses NVLink;
+//   (1) the 512 x 512 diagonal block is copied into a dense scratch stacked over an identity and factored
+//       right-looking with 128-blocks (potrf_inv + small DMMA products).  The same column operations applied
+//       to the identity rows leave inv(L_512)^T there, for free;
+//   (2) ALL rows below are solved by ONE product  X = A inv(L_512)^T  on the tensor cores (int8 digit planes
+//       of A and of inv(L_512), K = N = 512), written straight into the tiled panel buffers.
+// The serial part per step is four potrfs + nine tiny products; the O(m 512^2) work is a single launch.
+// ---------------------------------------------------------------------------------------------
+constexpr int64_t WIDE = (int64_t)OUTER_BLOCKS * NB;   // 512
+static_assert(OUTER_BLOCKS == 4 && NB == 128, "wide panel phase is written for 4 x 128");
+
+__global__ void wide_load_kernel(Packed L, int64_t k0, int nq, double* __restrict__ D) {
+    const int c = blockIdx.x;              // column inside the step
+    const int64_t g0 = k0 * NB;
+    for (int r = threadIdx.x; r < 2 * WIDE; r += blockDim.x) {
+        double v = 0.0;
+        if (r < nq * NB) {
+            if (r / NB >= c / NB) v = *L.at(g0 + r, g0 + c);
+        } else if (r >= WIDE && r - WIDE == c) {
+            v = 1.0;
+        }
+        D[(int64_t)c * (2 * WIDE) + r] = v;
+    }
+}
+
+// the sub-diagonal blocks of the factored diagonal block go back into the packed matrix
+__global__ void wide_store_kernel(Packed L, int64_t k0, int nq, const double* __restrict__ X) {
+    const int c = blockIdx.x;
+    const int64_t g0 = k0 * NB;
+    for (int r = threadIdx.x; r < nq * NB; r += blockDim.x)
+        if (r / NB > c / NB) *L.at(g0 + r, g0 + c) = X[(int64_t)c * (2 * WIDE) + r];
+}
+
+static int32_t p2p_exchange_col(sb_ctx* c, sb_factor* f, P2PRun& R, int64_t k, cudaStream_t st) {
+    const int owner = (int)(k % c->world), s = (int)(k % P2P_SLOTS);
+    const size_t bytes = (size_t)f->L.ld(k) * NB * sizeof(double);   // the block column is one contiguous slab
+    double* col = f->L.blk(k, k);
+    if (owner == c->rank) {
+        SB_TRY(p2p_slot_guard(c, R, k, st));
+        SB_CUDA(cudaMemcpyAsync(R.slot(c->p2p.arena, s), col, bytes, cudaMemcpyDeviceToDevice, st));
+        p2p_signal_kernel<<<1, 32, 0, st>>>(R.peers, c->world, c->rank, P2P_READY + c->rank, R.ord[k], -1);
+    } else {
+        p2p_wait_kernel<<<1, 32, 0, st>>>(R.ctr(c), P2P_READY + owner, 1, -1, R.ord[k], R.ctr(c) + P2P_ERR);
+        SB_CUDA(cudaMemcpyAsync(col, R.slot(c->p2p.peer[owner], s), bytes, cudaMemcpyDeviceToDevice, st));
+        p2p_signal_kernel<<<1, 32, 0, st>>>(R.peers, c->world, c->rank, P2P_ACK + c->rank, R.ord[k], owner);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// Serial part of the wide panel phase (panel stream): column exchange, the 512 x 512 diagonal block, inv(L_512)
+// and its digit planes.  Only small kernels: it runs on the few SMs the first part of T^B leaves free.
+static int32_t wide_diag_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, int rank, int world, cudaStream_t st,
+                               std::vector<CommEv>* comm_ev, P2PRun* R) {
+    const int64_t nblk = f->L.nblk();
+    const bool bulk = nblk - (k0 + nq) > 0;            // rows under the step (then nq == OUTER_BLOCKS)
+    if (world > 1) {
+        if (!(R && R->on)) {
+            sb::set_error("wide panel phase needs the peer-to-peer arena");
+            return SB_ERR_UNSUPPORTED;
+        }
+        CommEv ce{nullptr, nullptr};
+        if (comm_ev && c->fine_timing) {
+            ce.a = c->next_event(); ce.b = c->next_event();
+            SB_CUDA(cudaEventRecord(ce.a, st));
+        }
+        for (int q = 0; q < nq; q++) SB_TRY(p2p_exchange_col(c, f, *R, k0 + q, st));
+        if (ce.a) { SB_CUDA(cudaEventRecord(ce.b, st)); comm_ev->push_back(ce); }
+    }
+    double* Din = f->wide_D;
+    double* X = f->wide_D + 2 * WIDE * WIDE;
+    const int64_t ldd = 2 * WIDE;
+    wide_load_kernel<<<nq * NB, 256, 0, st>>>(f->L, k0, nq, Din);
+    const int64_t rtot = bulk ? 2 * WIDE : (int64_t)nq * NB;     // rows of the scratch that take part
+    for (int q = 0; q < nq; q++) {
+        const int64_t kq = k0 + q;
+        const int64_t dq = (int64_t)q * NB + (int64_t)q * NB * ldd;   // block (q, q)
+        launch_potrf_inv(f->L, kq, f->N, f->invL, f->logdet_blk, f->info_dev, st, f->ldiag, Din + dq, ldd);
+        const int64_t mq = rtot - (q + 1) * NB;
+        if (mq > 0)
+            launch_gemm_nt(Din + dq + NB, ldd, f->invL + kq * (int64_t)NB * NB, NB, X + dq + NB, ldd, mq, NB, NB, 1.0, 0.0, st);
+        for (int q2 = q + 1; q2 < nq; q2++) {
+            const int64_t xo = (int64_t)q2 * NB + (int64_t)q * NB * ldd;       // X rows from block q2 down, column q
+            const int64_t co = (int64_t)q2 * NB + (int64_t)q2 * NB * ldd;      // block (q2, q2) and below
+            launch_gemm_nt(X + xo, ldd, X + xo, ldd, Din + co, ldd, rtot - q2 * NB, NB, NB, -1.0, 1.0, st);
+        }
+    }
+    wide_store_kernel<<<nq * NB, 256, 0, st>>>(f->L, k0, nq, X);
+    SB_CUDA(cudaGetLastError());
+    if (!bulk) return SB_OK;
+    // inv(L_512)[n, k] = (identity rows of X)[k, n]
+    launch_transpose(X + WIDE, ldd, WIDE, WIDE, f->wide_W, WIDE, st);
+    OzSrc ws{};
+    ws.nseg = OUTER_BLOCKS;
+    for (int q = 0; q < OUTER_BLOCKS; q++) { ws.base[q] = f->wide_W + (int64_t)q * NB * WIDE; ws.ld[q] = WIDE; ws.rbs[q] = NB; }
+    launch_oz_slice(ws, 0, OUTER_BLOCKS, 0, WIDE, f->wide_wscale, f->wide_wexpo, f->wide_wp, st);
+    return SB_OK;
+}
+
+// Parallel part (trailing stream, whole GPU): digit planes of the un-normalised columns, the panel solve
+// X = A inv(L_512)^T on the tensor cores (K blocks above the diagonal of inv(L_512) skipped) written over the
+// columns in the packed matrix, digit planes of X for the trailing updates.  `set`: the digit-plane set of this
+// step (it first holds the planes of A, then those of X).
+static int32_t wide_bulk_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, int set, cudaStream_t st) {
+    const int64_t nblk = f->L.nblk(), Np = f->Np;
+    const int64_t below = nblk - (k0 + nq);
+    if (below <= 0) return SB_OK;
+    OzSrc as{};
+    as.nseg = OUTER_BLOCKS;
+    const int64_t r0 = k0 + OUTER_BLOCKS;              // first block row under the step
+    double* xcol[OUTER_BLOCKS];
+    int64_t ldx[OUTER_BLOCKS];
+    for (int q = 0; q < OUTER_BLOCKS; q++) {
+        xcol[q] = f->L.blk(r0, k0 + q); ldx[q] = f->L.ld(k0 + q);
+        as.base[q] = xcol[q]; as.ld[q] = ldx[q]; as.rbs[q] = NB;
+    }
+    launch_oz_slice(as, 0, below, r0 * NB, Np, f->oz_scale[set], f->oz_expo[set], f->oz_planes[set], st);
+    if (launch_panel_solve_ozaki(xcol, ldx, below * NB, &f->oz_maps[set], f->oz_scale[set], r0 * NB, &f->wide_wmaps,
+                                 f->wide_wscale, &f->oz_desc, st) != 0) {
+        sb::set_error("tcgen05 panel solve failed to launch");
+        return SB_ERR_CUDA;
+    }
+    launch_oz_slice(as, 0, below, r0 * NB, Np, f->oz_scale[set], f->oz_expo[set], f->oz_planes[set], st);
+    SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
 
@@ -444,6 +826,17 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
     for (int set = 0; set < 2; set++)
         for (int q = 0; q < OUTER_BLOCKS; q++)
             Pt[set][q] = Pw[set][q] = f->panel + (int64_t)(set * OUTER_BLOCKS + q) * tiled_panel_elems(Np);
+    P2PRun R;
+    if (world > 1 && c->p2p.state == 1) {   // panels move by peer copies through the IPC-mapped arena
+        R.on = true;
+        R.slot_elems = tiled_panel_elems(Np);
+        for (int r = 0; r < 8; r++) R.peers.base[r] = c->p2p.peer[r];
+        R.ord.resize(nblk);
+        R.guarded = c->p2p.pub[rank];
+        for (int64_t k = 0; k < nblk; k++) R.ord[k] = ++c->p2p.pub[k % world];
+        for (int set = 0; set < 2; set++)   // the arena slots ARE the tiled panel buffers
+            for (int q = 0; q < OUTER_BLOCKS; q++) Pt[set][q] = Pw[set][q] = R.slot(c->p2p.arena, set * OUTER_BLOCKS + q);
+    }
     std::vector<cudaEvent_t> ev_p(nsteps), ev_a(nsteps), ev_t0(nsteps), ev_t1(nsteps);
     for (int64_t s = 0; s < nsteps; s++) {
         ev_p[s] = c->next_event(); ev_a[s] = c->next_event(); ev_t0[s] = c->next_event(); ev_t1[s] = c->next_event();
@@ -452,9 +845,13 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
     // stream 2 starts after everything already queued on stream 1 (assembly)
     SB_CUDA(cudaEventRecord(e_start, s1));
     SB_CUDA(cudaStreamWaitEvent(s2, e_start, 0));
+    if (R.on) {   // every panel this rank published in earlier factorisations has been pulled by everyone
+        p2p_wait_kernel<<<1, 32, 0, s2>>>(R.ctr(c), P2P_ACK, world, rank, R.guarded, R.ctr(c) + P2P_ERR);
+        SB_CUDA(cudaGetLastError());
+    }
     {
         const int nq0 = (int)(nblk < OUTER_BLOCKS ? nblk : OUTER_BLOCKS);
-        SB_TRY(panel_phase(c, f, 0, nq0, Pw[0], Pt[0], rank, world, s2, &comm_ev));
+        SB_TRY(panel_phase(c, f, 0, nq0, Pw[0], Pt[0], rank, world, s2, &comm_ev, &R));
         if (f->oz)
             launch_oz_slice(oz_src_tiled(Pt[0], nq0), nq0 - 1, nblk - nq0, (int64_t)NB, Np, f->oz_scale[0], f->oz_expo[0],
                             f->oz_planes[0], s2);
@@ -490,7 +887,7 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
                 SB_CUDA(cudaStreamWaitEvent(s2, ev_a[s], 0));
                 CommEv ch{nullptr, nullptr};
                 if (c->fine_timing) { ch.a = c->next_event(); ch.b = c->next_event(); SB_CUDA(cudaEventRecord(ch.a, s2)); }
-                SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2, &comm_ev));
+                SB_TRY(panel_phase(c, f, jt, nq1, Pw[set ^ 1], Pt[set ^ 1], rank, world, s2, &comm_ev, &R));
                 if (f->oz)  // digit planes of the trailing rows of the panels just factored (block rows >= jt + nq1)
                     launch_oz_slice(oz_src_tiled(Pt[set ^ 1], nq1), nq1 - 1, nblk - (jt + nq1), (jt + 1) * (int64_t)NB, Np,
                                     f->oz_scale[set ^ 1], f->oz_expo[set ^ 1], f->oz_planes[set ^ 1], s2);
@@ -500,8 +897,13 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
             if (jA < nblk) {                                                                // T^B
                 const double tilesB = 2.0 * (double)syrk_packed_tiles(nblk, k0, jA, nblk, rank, world);
                 const int nq1 = (int)(nblk - jt < OUTER_BLOCKS ? nblk - jt : OUTER_BLOCKS);
-                const int reserve = (s + 1 < nsteps)
+                // T^B next to a panel phase: either a persistent grid that leaves `reserve` SMs free, or
+                // (tcgen05 path, SB_OZ_CHUNK > 0) short-lived CTAs of `chunk` tiles each, which hand SMs to
+                // the high-priority panel stream as they retire.
+                static const int chunk_env = getenv("SB_OZ_CHUNK") ? atoi(getenv("SB_OZ_CHUNK")) : 0;
+                int reserve = (s + 1 < nsteps)
                     ? pick_lookahead_sms(c->num_sms, tilesB, f->oz, nq1, Np - (jt + 1) * NB, world) : 0;
+                if (reserve > 0 && f->oz && chunk_env > 0) reserve = -chunk_env;
                 SB_TRY(trailing(jA, nblk, reserve));
             }
             int64_t tiles = syrk_packed_tiles(nblk, k0, jt, nblk, rank, world);
@@ -513,6 +915,14 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
     SB_CUDA(cudaStreamWaitEvent(s1, e_pend, 0));
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaStreamSynchronize(s1));
+    if (R.on) {
+        uint32_t err = 0;
+        SB_CUDA(cudaMemcpy(&err, R.ctr(c) + P2P_ERR, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            sb::set_error("peer-to-peer panel exchange timed out (a peer rank stopped making progress)");
+            return SB_ERR_NCCL;
+        }
+    }
     if (c->fine_timing) {
         for (int64_t s = 0; s < nsteps; s++) {
             float ms = 0;
@@ -542,6 +952,146 @@ static int32_t cholesky_lookahead(sb_ctx* c, sb_factor* f, int world, int rank) 
     return SB_OK;
 }
 
+// Factorisation with the wide panel phase (tcgen05 path).  Per outer step s, on the trailing stream:
+//   T^A_s | T^B_s part 1 (leaves a few SMs free) | panel solve of step s+1 (whole GPU) | T^B_s part 2 (whole GPU)
+// and on the panel stream, under T^B_s part 1: column exchange + diagonal block + inv(L_512) of step s+1.
+// Part 1 is sized to the duration of that serial chain, so the SM reservation costs ~ (8 / 148) x 1 ms per step.
+static int32_t cholesky_wide(sb_ctx* c, sb_factor* f, int world, int rank) {
+    const int64_t nblk = f->L.nblk(), Np = f->Np;
+    std::vector<CommEv> comm_ev, chain_ev, bulk_ev;
+    cudaStream_t s1 = c->stream, s2 = c->stream2;
+    const int64_t nsteps = (nblk + OUTER_BLOCKS - 1) / OUTER_BLOCKS;
+    P2PRun R;
+    if (world > 1) {
+        R.on = true;
+        R.slot_elems = tiled_panel_elems(Np);
+        for (int r = 0; r < 8; r++) R.peers.base[r] = c->p2p.peer[r];
+        R.ord.resize(nblk);
+        R.guarded = c->p2p.pub[rank];
+        for (int64_t k = 0; k < nblk; k++) R.ord[k] = ++c->p2p.pub[k % world];
+    }
+    std::vector<cudaEvent_t> ev_d(nsteps), ev_a(nsteps), ev_t0(nsteps), ev_t1(nsteps);
+    for (int64_t s = 0; s < nsteps; s++) {
+        ev_d[s] = c->next_event(); ev_a[s] = c->next_event(); ev_t0[s] = c->next_event(); ev_t1[s] = c->next_event();
+    }
+    cudaEvent_t e_start = c->next_event(), e_pend = c->next_event();
+    SB_CUDA(cudaEventRecord(e_start, s1));
+    SB_CUDA(cudaStreamWaitEvent(s2, e_start, 0));
+    if (R.on) {   // every column this rank published in earlier factorisations has been pulled by everyone
+        p2p_wait_kernel<<<1, 32, 0, s2>>>(R.ctr(c), P2P_ACK, world, rank, R.guarded, R.ctr(c) + P2P_ERR);
+        SB_CUDA(cudaGetLastError());
+    }
+    static const int r_env = getenv("SB_LOOKAHEAD_SMS") ? atoi(getenv("SB_LOOKAHEAD_SMS")) : 0;
+    static const int p1_env = getenv("SB_WIDE_P1_US") ? atoi(getenv("SB_WIDE_P1_US")) : 0;
+    const int reserve_p1 = r_env > 0 ? r_env : LOOKAHEAD_SMS;
+    const double chain_us = p1_env > 0 ? (double)p1_env : (world > 1 ? 1500.0 : 1000.0);
+    const int64_t p1_tiles = (int64_t)(chain_us / 14.5 * (c->num_sms - reserve_p1));   // half-tiles T^B part 1 should last
+
+    auto bulk = [&](int64_t s) -> int32_t {      // panel solve + digit planes of step s, trailing stream
+        const int64_t k0 = s * OUTER_BLOCKS;
+        const int nq = (int)(nblk - k0 < OUTER_BLOCKS ? nblk - k0 : OUTER_BLOCKS);
+        const int set = (int)(s & 1);
+        SB_CUDA(cudaStreamWaitEvent(s1, ev_d[s], 0));
+        CommEv be{nullptr, nullptr};
+        if (c->fine_timing) { be.a = c->next_event(); be.b = c->next_event(); SB_CUDA(cudaEventRecord(be.a, s1)); }
+        SB_TRY(wide_bulk_phase(c, f, k0, nq, set, s1));
+        if (be.a) { SB_CUDA(cudaEventRecord(be.b, s1)); bulk_ev.push_back(be); }
+        return SB_OK;
+    };
+    auto diag = [&](int64_t s) -> int32_t {      // serial part of step s, panel stream
+        const int64_t k0 = s * OUTER_BLOCKS;
+        const int nq = (int)(nblk - k0 < OUTER_BLOCKS ? nblk - k0 : OUTER_BLOCKS);
+        CommEv ch{nullptr, nullptr};
+        if (c->fine_timing) { ch.a = c->next_event(); ch.b = c->next_event(); SB_CUDA(cudaEventRecord(ch.a, s2)); }
+        SB_TRY(wide_diag_phase(c, f, k0, nq, rank, world, s2, &comm_ev, &R));
+        SB_CUDA(cudaEventRecord(ev_d[s], s2));
+        if (ch.a) { SB_CUDA(cudaEventRecord(ch.b, s2)); chain_ev.push_back(ch); }
+        return SB_OK;
+    };
+    SB_TRY(diag(0));
+    SB_TRY(bulk(0));
+    double flops = 0;
+    int64_t nlaunch = 0;
+    for (int64_t s = 0; s < nsteps; s++) {
+        const int64_t k0 = s * OUTER_BLOCKS;
+        const int nq = (int)(nblk - k0 < OUTER_BLOCKS ? nblk - k0 : OUTER_BLOCKS);
+        const int set = (int)(s & 1);
+        const int64_t jt = k0 + nq;
+        SB_CUDA(cudaEventRecord(ev_t0[s], s1));
+        if (jt < nblk) {
+            const int64_t jA = jt + OUTER_BLOCKS < nblk ? jt + OUTER_BLOCKS : nblk;
+            auto trailing = [&](int64_t jlo, int64_t jhi, int reserve, int64_t lo, int64_t hi) -> int32_t {
+                if (launch_syrk_ozaki(f->L, k0, nq, jlo, jhi, rank, world, &f->oz_maps[set], f->oz_scale[set], &f->oz_desc,
+                                      f->oz_mode, s1, reserve, nullptr, lo, hi) != 0) {
+                    sb::set_error("tcgen05 trailing kernel could not be launched");
+                    return SB_ERR_CUDA;
+                }
+                return SB_OK;
+            };
+            SB_TRY(trailing(jt, jA, 0, 0, 0));                     // T^A: the next step's block columns
+            SB_CUDA(cudaEventRecord(ev_a[s], s1));
+            const bool next = s + 1 < nsteps;
+            if (next) {
+                SB_CUDA(cudaStreamWaitEvent(s2, ev_a[s], 0));
+                SB_TRY(diag(s + 1));
+            }
+            const int64_t tilesB = jA < nblk ? 2 * syrk_packed_tiles(nblk, k0, jA, nblk, rank, world) : 0;
+            const int64_t n1 = next ? (tilesB < p1_tiles + 2 * c->num_sms ? tilesB : p1_tiles) : tilesB;
+            if (n1 > 0) SB_TRY(trailing(jA, nblk, next ? reserve_p1 : 0, 0, n1));          // T^B part 1
+            if (next) SB_TRY(bulk(s + 1));
+            if (tilesB > n1) SB_TRY(trailing(jA, nblk, 0, n1, tilesB));                      // T^B part 2
+            const int64_t tiles = syrk_packed_tiles(nblk, k0, jt, nblk, rank, world);
+            if (tiles > 0) { flops += (double)tiles * 2.0 * NB * NB * ((double)nq * NB); nlaunch++; }
+        }
+        SB_CUDA(cudaEventRecord(ev_t1[s], s1));
+    }
+    SB_CUDA(cudaEventRecord(e_pend, s2));
+    SB_CUDA(cudaStreamWaitEvent(s1, e_pend, 0));
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(s1));
+    if (R.on) {
+        uint32_t err = 0;
+        SB_CUDA(cudaMemcpy(&err, R.ctr(c) + P2P_ERR, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            sb::set_error("peer-to-peer column exchange timed out (a peer rank stopped making progress)");
+            return SB_ERR_NCCL;
+        }
+    }
+    if (c->fine_timing) {
+        double tr = 0, bk = 0;
+        for (int64_t s = 0; s < nsteps; s++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_t0[s], ev_t1[s]);
+            tr += ms;
+        }
+        for (size_t i = 0; i < bulk_ev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, bulk_ev[i].a, bulk_ev[i].b);
+            if (i > 0) bk += ms;               // the first panel solve lies before ev_t0[0]
+            c->tm.panel_ms += ms;              // panel solves are on the critical path (whole GPU, ~0.4 ms each)
+        }
+        c->tm.trailing_ms += tr - bk;
+        c->tm.trailing_kernel_ms += tr - bk;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e_start, ev_d[0]);
+        c->tm.panel_ms += ms;                  // the first serial phase is not hidden
+        for (auto& ce : comm_ev) {             // column exchange incl. waiting for the owners' T^A
+            float cm = 0;
+            cudaEventElapsedTime(&cm, ce.a, ce.b);
+            c->tm.comm_ms += cm;
+        }
+        for (auto& ce : chain_ev) {
+            float cm = 0;
+            cudaEventElapsedTime(&cm, ce.a, ce.b);
+            c->tm.panel_chain_ms += cm;
+        }
+    }
+    c->tm.trailing_flops += flops;
+    c->tm.trailing_launches += nlaunch;
+    c->tm.trailing_int8_ops += 28.0 * flops;
+    return SB_OK;
+}
+
 static int32_t sync_info(sb_ctx* c, sb_factor* f);
 
 int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
@@ -555,7 +1105,9 @@ int32_t cholesky_packed(sb_ctx* c, sb_factor* f, bool force_local = false) {
     static const bool no_la = getenv("SB_NO_LOOKAHEAD") != nullptr;
     static const bool force_la = getenv("SB_FORCE_LOOKAHEAD") != nullptr;
     if (!no_la && nblk > OUTER_BLOCKS && (world > 1 || f->oz || force_la)) {
-        SB_TRY(cholesky_lookahead(c, f, world, rank));
+        if (world > 1) SB_TRY(p2p_ensure(c, f->Np));
+        if (f->wide && (world == 1 || c->p2p.state == 1)) SB_TRY(cholesky_wide(c, f, world, rank));
+        else SB_TRY(cholesky_lookahead(c, f, world, rank));
         if (world > 1) {
             SB_TRY(sync_info(c, f));
             SB_CUDA(cudaStreamSynchronize(c->stream));  // callers read info / logdet with blocking copies
@@ -720,7 +1272,11 @@ int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
     sb_ctx* c = new sb_ctx();
     c->device = device;
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    SB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    {   // the panel stream outranks the trailing-update stream: its kernels sit on the critical path
+        int prio_lo = 0, prio_hi = 0;
+        SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        SB_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
+    }
     const char* ft = getenv("SB_FINE_TIMING");
     if (ft && ft[0] == '0') c->fine_timing = false;
     SB_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -768,6 +1324,13 @@ int32_t sb_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const vo
 int32_t sb_ctx_destroy(sb_ctx* c) {
     if (!c) return SB_OK;
     cudaSetDevice(c->device);
+    if (c->p2p.arena) {   // collective, like the communicator: no peer may still be reading this arena
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->stream2);
+        if (c->comm && c->p2p.xch) nccl_barrier(c, static_cast<char*>(c->p2p.xch) + 8 * sizeof(cudaIpcMemHandle_t));
+        p2p_close(c);
+    }
+    if (c->p2p.xch) cudaFree(c->p2p.xch);
     if (c->comm) nccl_dl::CommDestroy(c->comm);
     c->pool_trim();
     for (auto e : c->ev) cudaEventDestroy(e);
@@ -883,6 +1446,14 @@ int32_t sb_factor_destroy(sb_factor* f) {
         c->pool_release(f->oz_scale[i], (size_t)f->Np * sizeof(double));
         c->pool_release(f->oz_expo[i], (size_t)f->Np * sizeof(int));
     }
+    {
+        constexpr int64_t WD = (int64_t)OUTER_BLOCKS * NB;
+        c->pool_release(f->wide_D, (size_t)2 * 2 * WD * WD * sizeof(double));
+        c->pool_release(f->wide_W, (size_t)WD * WD * sizeof(double));
+        c->pool_release(f->wide_wp, oz_planes_bytes(WD));
+        c->pool_release(f->wide_wscale, (size_t)WD * sizeof(double));
+        c->pool_release(f->wide_wexpo, (size_t)WD * sizeof(int));
+    }
     c->pool_release(f->sweep_flags, (size_t)2 * (f->Np / NB) * sizeof(unsigned));
     c->pool_release(f->vcache, (size_t)2 * f->Np * sizeof(double));
     c->pool_release(f->vcache_flag, sizeof(int));
@@ -943,6 +1514,21 @@ static int32_t factor_alloc(sb_ctx* c, int64_t N, sb_factor** out) {
                 return SB_ERR_CUDA;
             }
             f->oz = true;
+            static const bool no_wide = getenv("SB_WIDE_PANEL") && getenv("SB_WIDE_PANEL")[0] == '0';
+            if (!no_wide && (f->oz_mode >= 16 || (f->oz_mode & 3) == 0)) {   // the panel solve instance needs SWIZZLE_64B maps
+                constexpr int64_t WD = (int64_t)OUTER_BLOCKS * NB;
+                e = c->pool_alloc((void**)&f->wide_D, (size_t)2 * 2 * WD * WD * sizeof(double));
+                if (e == cudaSuccess) e = c->pool_alloc((void**)&f->wide_W, (size_t)WD * WD * sizeof(double));
+                if (e == cudaSuccess) e = c->pool_alloc((void**)&f->wide_wp, oz_planes_bytes(WD));
+                if (e == cudaSuccess) e = c->pool_alloc((void**)&f->wide_wscale, (size_t)WD * sizeof(double));
+                if (e == cudaSuccess) e = c->pool_alloc((void**)&f->wide_wexpo, (size_t)WD * sizeof(int));
+                if (e == cudaSuccess && oz_make_maps(f->wide_wp, WD, f->oz_mode, &f->wide_wmaps) != 0) {
+                    sb_factor_destroy(f);
+                    sb::set_error("cuTensorMapEncodeTiled failed for the inv(L_512) digit planes");
+                    return SB_ERR_CUDA;
+                }
+                f->wide = e == cudaSuccess;
+            }
         }
     }
     if (e != cudaSuccess) {

@@ -56,6 +56,9 @@ struct OzArgs {
     Packed Pk;
     int64_t J0, w;    // packed: first owned trailing block column, column stride (world)
     int64_t total_tiles;
+    int64_t tile_lo, tile_hi;   // this launch covers tiles [tile_lo, tile_hi) of the list (a trailing update can be split)
+    int tri;             // plain mode: B is block lower triangular (128-blocks): column block q only needs K <= 128 (q + 1)
+    int tiles_per_cta;   // 0: persistent CTAs (tile t = blockIdx.x + i*gridDim.x); > 0: CTA b owns tiles [b*tpc, (b+1)*tpc)
     int kchunks;      // K / KC
     const double* scaleA;  // row scales s_i = 2^(e_i - 31), indexed by plane row of A / B
     const double* scaleB;
@@ -63,6 +66,13 @@ struct OzArgs {
     double* C;
     int64_t ldc, mtiles;
     int64_t rowA0, rowB0;
+    // plain mode C addressing: tile (rt, ct) starts at C + rt*c_rt_stride + (ct/2)*c_pair_stride + (ct%2)*64*ldc
+    // (dense column-major: 128, 128*ldc; TILED Cholesky panels: 128*132, distance between panel buffers, ldc 132)
+    int64_t c_rt_stride, c_pair_stride;
+    int store;        // 0: C -= s_i s_j acc;  1 (separate kernel instance): C = + s_i s_j acc, no read, and
+                      // column block q = ct / 2 of C has its own base / leading dimension (the packed matrix's block columns)
+    double* cb[4];
+    int64_t cld[4];
     // shared-memory matrix descriptor fields (runtime so the test harness can probe encodings)
     uint32_t a_kk_adv, b_kk_adv;  // start-address advance (16-byte units) per K=32 step
     uint32_t a_lbo, b_lbo, sbo;   // 16-byte units
@@ -182,6 +192,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
 
 // same enumeration as gemm_nt.cu's packed-SYRK cursor: owned block columns J0, J0+w, ...; column J
 // holds nblk-J row blocks, two 64-wide half tiles per block
+// Tile range of this CTA.  Persistent mode strides the whole list by gridDim.x; chunked mode gives every
+// CTA a short contiguous run and lets the CTA retire, so that kernels of a higher-priority stream (the
+// look-ahead panel phase and its NCCL broadcast) get SMs within microseconds instead of waiting for a
+// persistent grid to finish (round-2 measurement: 0.6-1.2 ms per panel broadcast next to a persistent T^B).
+#ifdef OZ_EXP_NO_CHUNK
+__device__ __forceinline__ int64_t oz_t_begin(const OzArgs& g) { return g.tile_lo + (int64_t)blockIdx.x; }
+__device__ __forceinline__ int64_t oz_t_end(const OzArgs& g) { return g.tile_hi; }
+__device__ __forceinline__ int64_t oz_t_step(const OzArgs& g) { return (int64_t)gridDim.x; }
+#else
+__device__ __forceinline__ int64_t oz_t_begin(const OzArgs& g) {
+    return g.tile_lo + (g.tiles_per_cta > 0 ? (int64_t)blockIdx.x * g.tiles_per_cta : (int64_t)blockIdx.x);
+}
+__device__ __forceinline__ int64_t oz_t_end(const OzArgs& g) {
+    if (g.tiles_per_cta <= 0) return g.tile_hi;
+    const int64_t e = g.tile_lo + ((int64_t)blockIdx.x + 1) * g.tiles_per_cta;
+    return e < g.tile_hi ? e : g.tile_hi;
+}
+__device__ __forceinline__ int64_t oz_t_step(const OzArgs& g) { return g.tiles_per_cta > 0 ? 1 : (int64_t)gridDim.x; }
+#endif
+
+// K chunks of tile t (KC bytes each): all of K, or -- triangular B -- only the blocks up to the tile's column block
+template <int KC>
+__device__ __forceinline__ int oz_tile_kchunks(const OzArgs& g, int64_t t) {
+    if (!g.tri) return g.kchunks;
+    const int64_t ct = t / g.mtiles;
+    return (int)((ct >> 1) + 1) * (NB / KC);
+}
+
 struct OzTile {
     int rowA, rowB;    // first plane row of the A (128 rows) / B (64 rows) operand
     double* C;         // top-left element of the 128 x 64 output tile
@@ -221,7 +259,7 @@ struct OzCursor {
             o.rowA = (int)(g.rowA0 + rt * OZ_BM);
             o.rowB = (int)(g.rowB0 + ct * OZ_BN);
             o.ldc = g.ldc;
-            o.C = g.C + ct * OZ_BN * g.ldc + rt * OZ_BM;
+            o.C = g.C + (ct >> 1) * g.c_pair_stride + (ct & 1) * OZ_BN * g.ldc + rt * g.c_rt_stride;
         }
         return o;
     }
@@ -242,13 +280,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 // Epilogue of both kernel variants (warps 0..7): drain the seven int32 accumulators of each tile from
 // TMEM, weight + sum them in fp64 registers, release each accumulator right after its tcgen05.ld, then
 // C -= s_i s_j acc on the fp64 matrix.
+template <bool STORE>
 __device__ __forceinline__ void oz_epilogue(const OzArgs& g, uint32_t tmem, uint32_t tfull0, uint32_t tempty0, int warp,
                                             int lane) {
         const int lq = warp & 3, ch = warp >> 2;  // TMEM lane quarter (hardware: warp % 4), column half
         OzCursor cur;
-        cur.init(g, blockIdx.x);
+        cur.init(g, oz_t_begin(g));
         uint32_t it = 0;
-        for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x), it++) {
+        const int64_t t_end = oz_t_end(g), t_step = oz_t_step(g);
+        for (; cur.t < t_end; cur.advance(g, t_step), it++) {
             const OzTile tl = cur.tile(g);
             double acc[32];
 #pragma unroll
@@ -283,6 +323,14 @@ __device__ __forceinline__ void oz_epilogue(const OzArgs& g, uint32_t tmem, uint
 #ifdef OZ_ABLATE_NO_C
             continue;
 #endif
+            if constexpr (STORE) {   // panel solve X = A W^T written straight into the packed matrix: no read of C
+                const int64_t rt = cur.t % g.mtiles, ct = cur.t / g.mtiles;
+                const int64_t ldq = g.cld[ct >> 1];
+                double* xp = g.cb[ct >> 1] + ((ct & 1) * OZ_BN + ch * 32) * ldq + rt * OZ_BM + row;
+#pragma unroll
+                for (int c = 0; c < 32; c++) xp[(int64_t)c * ldq] = (si * sj[c]) * acc[c];
+                continue;
+            }
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 8) {
                 double old[8];
@@ -294,7 +342,7 @@ __device__ __forceinline__ void oz_epilogue(const OzArgs& g, uint32_t tmem, uint
         }
 }
 
-template <int KC, int STAGES, int TMODE, bool ATMEM, bool PAIR>
+template <int KC, int STAGES, int TMODE, bool ATMEM, bool PAIR, bool STORE = false>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUtensorMap tmA,
                   const __grid_constant__ CUtensorMap tmB) {
@@ -349,12 +397,14 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
         // ===================== TMA producer =====================
         if (lane == 0) {
             OzCursor cur;
-            cur.init(g, blockIdx.x);
+            cur.init(g, oz_t_begin(g));
             uint32_t n = 0;
-            for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x)) {
+            const int64_t t_end = oz_t_end(g), t_step = oz_t_step(g);
+            for (; cur.t < t_end; cur.advance(g, t_step)) {
                 const OzTile tl = cur.tile(g);
                 const int rowA = tl.rowA, rowB = tl.rowB;
-                for (int kc = 0; kc < g.kchunks; kc++, n++) {
+                const int kch = oz_tile_kchunks<OZ_KC>(g, cur.t);
+                for (int kc = 0; kc < kch; kc++, n++) {
                     const uint32_t st = n % OZ_STAGES, ph = (n / OZ_STAGES) & 1;
 #ifdef OZ_ABLATE_NO_TMA
                     continue;
@@ -384,8 +434,10 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
         constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
                                    ((uint32_t)(OZ_BM >> 4) << 24);
         uint32_t n = 0, it = 0;
-        for (int64_t t = blockIdx.x; t < g.total_tiles; t += gridDim.x, it++) {
-            for (int kc = 0; kc < g.kchunks; kc++, n++) {
+        const int64_t t_end = oz_t_end(g), t_step = oz_t_step(g);
+        for (int64_t t = oz_t_begin(g); t < t_end; t += t_step, it++) {
+            const int kch = oz_tile_kchunks<OZ_KC>(g, t);
+            for (int kc = 0; kc < kch; kc++, n++) {
                 const uint32_t st = n % OZ_STAGES, ph = (n / OZ_STAGES) & 1;
 #ifndef OZ_ABLATE_NO_TMA
                 mbar_wait(full0 + 8 * st, ph);
@@ -424,7 +476,7 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                             }
                         }
                     }
-                    if (kc == g.kchunks - 1 && leader) {
+                    if (kc == kch - 1 && leader) {
 #pragma unroll
                         for (int grp = 0; grp < OZ_S; grp++) tc_commit(tfull0 + 8 * grp);
                     }
@@ -448,7 +500,7 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
 #endif
                             }
                         }
-                        if (kc == g.kchunks - 1 && leader) tc_commit(tfull0 + 8 * grp);   // G_{grp+2} of this tile is final
+                        if (kc == kch - 1 && leader) tc_commit(tfull0 + 8 * grp);   // G_{grp+2} of this tile is final
                     }
                 } else {
                     // A operand through TMEM: the 7 digit planes of one K = 32 step are copied smem -> TMEM
@@ -481,7 +533,7 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                                         mma_i8_ts(d, tmem + A_TMEM_COL + (uint32_t)p * 8, blo, D_HI, idesc,
                                                   (p > 0 || kk > 0) ? 1u : acc0);
                                 }
-                                if (kc == g.kchunks - 1 && kk == OZ_KC / 32 - 1 && leader) tc_commit(tfull0 + 8 * grp);
+                                if (kc == kch - 1 && kk == OZ_KC / 32 - 1 && leader) tc_commit(tfull0 + 8 * grp);
                             }
                         } else {
                             // A from TMEM AND two B planes per instruction (N = 128)
@@ -503,7 +555,7 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                                                   two ? idesc128 : idesc, (p > 0 || kk > 0) ? 1u : acc0);
                                 }
                             }
-                            if (kc == g.kchunks - 1 && kk == OZ_KC / 32 - 1 && leader) {
+                            if (kc == kch - 1 && kk == OZ_KC / 32 - 1 && leader) {
 #pragma unroll
                                 for (int grp = 0; grp < OZ_S; grp++) tc_commit(tfull0 + 8 * grp);
                             }
@@ -518,7 +570,7 @@ ozaki_syrk_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
         }
     } else {
         // ===================== epilogue warps 0..7 =====================
-        oz_epilogue(g, tmem, tfull0, tempty0, warp, lane);
+        oz_epilogue<STORE>(g, tmem, tfull0, tempty0, warp, lane);
     }
 
     tc_fence_before();
@@ -581,11 +633,13 @@ ozaki_ring_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
         // ===================== TMA producer =====================
         if (lane == 0) {
             OzCursor cur;
-            cur.init(g, blockIdx.x);
+            cur.init(g, oz_t_begin(g));
             uint32_t na = 0, nb = 0;
-            for (; cur.t < g.total_tiles; cur.advance(g, gridDim.x)) {
+            const int64_t t_end = oz_t_end(g), t_step = oz_t_step(g);
+            for (; cur.t < t_end; cur.advance(g, t_step)) {
                 const OzTile tl = cur.tile(g);
-                for (int kc = 0; kc < g.kchunks; kc++, nb++) {
+                const int kch = oz_tile_kchunks<RK>(g, cur.t);
+                for (int kc = 0; kc < kch; kc++, nb++) {
                     {
                         const uint32_t bs = nb % RING_B, ph = (nb / RING_B) & 1;
                         mbar_wait(emptyB + 8 * bs, ph ^ 1);
@@ -608,8 +662,10 @@ ozaki_ring_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
         constexpr uint32_t idesc64 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
         constexpr uint32_t idesc128 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
         uint32_t na = 0, nb = 0, it = 0;
-        for (int64_t t = blockIdx.x; t < g.total_tiles; t += gridDim.x, it++) {
-            for (int kc = 0; kc < g.kchunks; kc++, nb++) {
+        const int64_t t_end = oz_t_end(g), t_step = oz_t_step(g);
+        for (int64_t t = oz_t_begin(g); t < t_end; t += t_step, it++) {
+            const int kch = oz_tile_kchunks<RK>(g, t);
+            for (int kc = 0; kc < kch; kc++, nb++) {
                 const uint32_t bs = nb % RING_B;
                 mbar_wait(fullB + 8 * bs, (nb / RING_B) & 1);
                 const uint32_t b0 = ((sB0 + bs * RB_STAGE) >> 4) | (1u << 16);
@@ -639,7 +695,7 @@ ozaki_ring_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
                     if (leader) tc_commit(emptyA + 8 * sl);     // A plane slot free once these MMAs have read it
                 }
                 if (leader) tc_commit(emptyB + 8 * bs);
-                if (kc == g.kchunks - 1 && leader) {
+                if (kc == kch - 1 && leader) {
 #pragma unroll
                     for (int grp = 0; grp < OZ_S; grp++) tc_commit(tfull0 + 8 * grp);
                 }
@@ -647,7 +703,7 @@ ozaki_ring_kernel(const __grid_constant__ OzArgs g, const __grid_constant__ CUte
             }
         }
     } else {
-        oz_epilogue(g, tmem, tfull0, tempty0, warp, lane);
+        oz_epilogue<false>(g, tmem, tfull0, tempty0, warp, lane);
     }
 
     tc_fence_before();
@@ -751,6 +807,8 @@ int oz_init() {
         OZ_ATTR(64, 2, 0, false, false); OZ_ATTR(64, 2, 1, false, false); OZ_ATTR(32, 5, 2, false, false);
         OZ_ATTR(64, 2, 0, true, false); OZ_ATTR(32, 5, 2, true, false);
         OZ_ATTR(64, 2, 0, false, true); OZ_ATTR(32, 5, 2, false, true); OZ_ATTR(64, 2, 0, true, true);
+        if (cudaFuncSetAttribute(ozaki_syrk_kernel<64, 2, 0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)OzCfg<64, 2>::SMEM) != cudaSuccess) return -2;
         if (cudaFuncSetAttribute(ozaki_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM) != cudaSuccess) return -2;
 #undef OZ_ATTR
         int dev = 0;
@@ -862,12 +920,25 @@ static void oz_fill_desc(OzArgs& g, const OzDesc* desc, int tma_mode, int* dbg) 
 static int oz_launch(OzArgs& g, const OzMaps* mapsA, const OzMaps* mapsB, cudaStream_t s, int reserve_sms) {
     int64_t cap = g_oz_sms - reserve_sms;
     if (cap < 1) cap = 1;
-    const int64_t grid = g.total_tiles < cap ? g.total_tiles : cap;
+    if (g.tile_hi <= 0 || g.tile_hi > g.total_tiles) g.tile_hi = g.total_tiles;
+    if (g.tile_lo < 0) g.tile_lo = 0;
+    const int64_t ntiles = g.tile_hi - g.tile_lo;
+    if (ntiles <= 0) return 0;
+    int64_t grid = ntiles < cap ? ntiles : cap;
+    if (reserve_sms < 0) {   // chunked, non-persistent: -reserve_sms tiles per CTA (see oz_t_begin)
+        g.tiles_per_cta = -reserve_sms;
+        grid = (ntiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+    }
     const CUtensorMap* ma = reinterpret_cast<const CUtensorMap*>(mapsA->a);
     const CUtensorMap* mb = reinterpret_cast<const CUtensorMap*>(mapsB->b);
     if (g.tma_mode >= 16) {
         const CUtensorMap* m1 = reinterpret_cast<const CUtensorMap*>(mapsA->a1);
         ozaki_ring_kernel<<<(unsigned)grid, OZ_THREADS, RING_SMEM, s>>>(g, *m1, *mb);
+        g_launch_count++;
+        return 0;
+    }
+    if (g.store) {   // panel solve: one instance only (SWIZZLE_64B maps, paired N)
+        ozaki_syrk_kernel<64, 2, 0, false, true, true><<<(unsigned)grid, OZ_THREADS, OzCfg<64, 2>::SMEM, s>>>(g, *ma, *mb);
         g_launch_count++;
         return 0;
     }
@@ -882,7 +953,7 @@ static int oz_launch(OzArgs& g, const OzMaps* mapsA, const OzMaps* mapsB, cudaSt
 // the digit planes / scales produced by launch_oz_slice.  K = 128 * nseg.
 int launch_syrk_ozaki(Packed Apk, int64_t k, int nseg, int64_t jlo, int64_t jhi, int rank, int world,
                       const OzMaps* maps, const double* scale, const OzDesc* desc, int tma_mode, cudaStream_t s,
-                      int reserve_sms, int* dbg) {
+                      int reserve_sms, int* dbg, int64_t tile_lo, int64_t tile_hi) {
     if (oz_init() != 0) return -1;
     const int64_t nblk = Apk.nblk();
     if (jlo < k + 1) jlo = k + 1;
@@ -894,6 +965,7 @@ int launch_syrk_ozaki(Packed Apk, int64_t k, int nseg, int64_t jlo, int64_t jhi,
     g.mode = 1;
     g.Pk = Apk; g.J0 = J0; g.w = world;
     g.total_tiles = tiles * 2;
+    g.tile_lo = tile_lo; g.tile_hi = tile_hi;   // (0, 0): everything
     g.kchunks = nseg * NB / ((tma_mode < 16 && (tma_mode & 3) == 2) ? 32 : 64);
     g.scaleA = g.scaleB = scale;
     oz_fill_desc(g, desc, tma_mode, dbg);
@@ -911,12 +983,36 @@ int launch_gemm_ozaki(double* C, int64_t ldc, int64_t M, int64_t Ncols, int nseg
     OzArgs g{};
     g.mode = 0;
     g.C = C; g.ldc = ldc; g.mtiles = M / OZ_BM;
+    g.c_rt_stride = OZ_BM;
+    g.c_pair_stride = 2 * OZ_BN * ldc;
     g.total_tiles = (M / OZ_BM) * (Ncols / OZ_BN);
     g.kchunks = nseg * NB / ((tma_mode < 16 && (tma_mode & 3) == 2) ? 32 : 64);
     g.scaleA = scaleA; g.scaleB = scaleB;
     g.rowA0 = rowA0; g.rowB0 = rowB0;
     oz_fill_desc(g, desc, tma_mode, nullptr);
     return oz_launch(g, mapsA, mapsB, s, 0);
+}
+
+// Panel solve of the wide panel phase:  X[M x 512] = A W^T, W = inv(L_512) block lower triangular (K blocks above
+// the diagonal are skipped), written over the four block columns Xcol[q] (leading dimensions ldx[q]) the planes of A
+// were cut from.  Needs SWIZZLE_64B maps (tma_mode & 3 == 0).
+int launch_panel_solve_ozaki(double* const* Xcol, const int64_t* ldx, int64_t M, const OzMaps* mapsA, const double* scaleA,
+                             int64_t rowA0, const OzMaps* mapsW, const double* scaleW, const OzDesc* desc, cudaStream_t s) {
+    if (oz_init() != 0) return -1;
+    if (M <= 0) return 0;
+    OzArgs g{};
+    g.mode = 0;
+    g.mtiles = M / OZ_BM;
+    g.total_tiles = (M / OZ_BM) * (4 * NB / OZ_BN);
+    g.kchunks = 4 * NB / 64;
+    g.tri = 1;
+    g.store = 1;
+    for (int q = 0; q < 4; q++) { g.cb[q] = Xcol[q]; g.cld[q] = ldx[q]; }
+    g.C = Xcol[0]; g.ldc = ldx[0]; g.c_rt_stride = OZ_BM; g.c_pair_stride = 0;
+    g.scaleA = scaleA; g.scaleB = scaleW;
+    g.rowA0 = rowA0; g.rowB0 = 0;
+    oz_fill_desc(g, desc, 8, nullptr);
+    return oz_launch(g, mapsA, mapsW, s, 0);
 }
 
 }  // namespace sb

@@ -20,7 +20,7 @@ constexpr size_t POTRF_SMEM = (size_t)NB * LDS * 8 + (size_t)NPB * PB * PB * 8 +
 __global__ void __launch_bounds__(PT, 1)
 potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
                  double* __restrict__ logdet_blk, long long* __restrict__ info,
-                 double* __restrict__ ldiag) {
+                 double* __restrict__ ldiag, const double* __restrict__ src, int64_t ld_src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s = reinterpret_cast<double*>(smem_raw);   // s[c*LDS + r]: the block, column-major
     double* dinv = s + NB * LDS;                       // [NPB][PB*PB]: inverses of the 8x8 diagonal blocks (col-major)
@@ -32,9 +32,13 @@ potrf_inv_kernel(Packed A, int64_t k, int64_t N, double* __restrict__ invL,
     double* Akk = A.blk(k, k);
     const int64_t ld = A.ld(k);
 
+    // the block is read from `src` when given (wide panel phase: the step's dense diagonal scratch) and
+    // always written to the packed matrix
+    const double* Ain = src != nullptr ? src : Akk;
+    const int64_t ldin = src != nullptr ? ld_src : ld;
     for (int idx = tid; idx < NB * NB; idx += PT) {
         int r = idx % NB, c = idx / NB;
-        s[c * LDS + r] = (r >= c) ? Akk[(int64_t)c * ld + r] : 0.0;
+        s[c * LDS + r] = (r >= c) ? Ain[(int64_t)c * ldin + r] : 0.0;
     }
     if (tid == 0) *bad = 0;
     __syncthreads();
@@ -236,13 +240,13 @@ bool g_attr = false;
 }  // namespace
 
 void launch_potrf_inv(Packed A, int64_t k, int64_t N, double* invL, double* logdet_blk,
-                      long long* info, cudaStream_t st, double* ldiag) {
+                      long long* info, cudaStream_t st, double* ldiag, const double* src, int64_t ld_src) {
     if (!g_attr) {
         cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)POTRF_SMEM);
         g_attr = true;
     }
-    potrf_inv_kernel<<<1, PT, POTRF_SMEM, st>>>(A, k, N, invL, logdet_blk, info, ldiag);
+    potrf_inv_kernel<<<1, PT, POTRF_SMEM, st>>>(A, k, N, invL, logdet_blk, info, ldiag, src, ld_src);
     g_launch_count++;
 }
 

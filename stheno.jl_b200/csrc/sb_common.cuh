@@ -110,8 +110,10 @@ void launch_grad_reduce(const BlockDev& b, const double* alpha, const double* Ki
 // (dense NB x NB, ld NB) + per-block sum of log pivots + first failing pivot (1-based, 0 = ok)
 // ldiag != nullptr: also store a contiguous copy of L_kk at ldiag + k*NB*NB (multi-GPU: it is
 // broadcast together with the panel so every rank ends up with the complete factor)
+// src != nullptr: the input block is read from src (column-major, ld_src) instead of the packed matrix
 void launch_potrf_inv(Packed A, int64_t k, int64_t N, double* invL, double* logdet_blk,
-                      long long* info, cudaStream_t s, double* ldiag = nullptr);
+                      long long* info, cudaStream_t s, double* ldiag = nullptr, const double* src = nullptr,
+                      int64_t ld_src = 0);
 
 // C = beta*C + alpha * A * B^T  (all column-major), M x Ncols x K, multiples of 128 / 64 / 16
 void launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
@@ -185,12 +187,15 @@ void launch_oz_slice(const OzSrc& src, int64_t rb_lo, int64_t nrb, int64_t out_r
                      double* scale, int* expo, signed char* planes, cudaStream_t s);
 int launch_syrk_ozaki(Packed A, int64_t k, int nseg, int64_t jlo, int64_t jhi, int rank, int world,
                       const OzMaps* maps, const double* scale, const OzDesc* desc, int tma_mode, cudaStream_t s,
-                      int reserve_sms = 0, int* dbg = nullptr);
+                      int reserve_sms = 0, int* dbg = nullptr, int64_t tile_lo = 0, int64_t tile_hi = 0);
 
 // plain product C[M x Ncols] -= A B^T through the same kernel (dense column-major C)
 int launch_gemm_ozaki(double* C, int64_t ldc, int64_t M, int64_t Ncols, int nseg, const OzMaps* mapsA,
                       const double* scaleA, int64_t rowA0, const OzMaps* mapsB, const double* scaleB, int64_t rowB0,
                       const OzDesc* desc, int tma_mode, cudaStream_t s);
+// X = A inv(L_512)^T over four block columns of the packed matrix (wide panel phase, ozaki.cu)
+int launch_panel_solve_ozaki(double* const* Xcol, const int64_t* ldx, int64_t M, const OzMaps* mapsA, const double* scaleA,
+                             int64_t rowA0, const OzMaps* mapsW, const double* scaleW, const OzDesc* desc, cudaStream_t s);
 
 extern thread_local int64_t g_launch_count;
 

@@ -98,7 +98,11 @@ static void cpu_digits(const Problem& pr, int64_t i, std::vector<int>& d /*[7][K
         }
 }
 
+// OZ_TEST_RESERVE: > 0 leaves that many SMs free (persistent grid), < 0 launches chunked CTAs of -value tiles
+static int g_reserve = 0;
+
 int main(int argc, char** argv) {
+    if (getenv("OZ_TEST_RESERVE")) g_reserve = atoi(getenv("OZ_TEST_RESERVE"));
     const int64_t Np = argc > 1 ? atoll(argv[1]) : 4096;
     const int64_t NpT = argc > 2 ? atoll(argv[2]) : 0;
     const int nseg = argc > 3 ? atoi(argv[3]) : 4;
@@ -153,7 +157,7 @@ int main(int argc, char** argv) {
             oz_default_desc(&d, v.tma_mode);
             if (v.lbo_override >= 0) d.a_lbo = d.b_lbo = v.lbo_override;
             if (v.lbo_override == -2) { uint32_t a = d.a_lbo, b = d.b_lbo; d.a_lbo = d.b_lbo = d.sbo; d.sbo = a; (void)b; }
-            int rc = launch_syrk_ozaki(pr.P2, 0, nseg, jt, pr.nblk, 0, 1, &maps, pr.scale, &d, v.tma_mode, st, 0, dbg);
+            int rc = launch_syrk_ozaki(pr.P2, 0, nseg, jt, pr.nblk, 0, 1, &maps, pr.scale, &d, v.tma_mode, st, g_reserve, dbg);
             cudaError_t e = cudaStreamSynchronize(st);
             if (rc || e != cudaSuccess) {
                 printf("[%s] launch rc=%d, cuda: %s\n", v.name, rc, cudaGetErrorString(e));
@@ -231,7 +235,7 @@ int main(int argc, char** argv) {
             oz_default_desc(&d, mode);
             for (int rep = 0; rep < 3; rep++) {
                 cudaEventRecord(e0, st);
-                launch_syrk_ozaki(pr.P2, 0, nseg, jt, pr.nblk, 0, 1, &maps, pr.scale, &d, mode, st);
+                launch_syrk_ozaki(pr.P2, 0, nseg, jt, pr.nblk, 0, 1, &maps, pr.scale, &d, mode, st, g_reserve);
                 cudaEventRecord(e1, st);
                 cudaError_t e = cudaStreamSynchronize(st);
                 if (e != cudaSuccess) { printf("ozaki timing run failed: %s\n", cudaGetErrorString(e)); return 3; }
