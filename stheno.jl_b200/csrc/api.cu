@@ -92,6 +92,7 @@ struct sb_ctx {
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // look-ahead panel stream (multi-GPU)
+    cudaStream_t xstream[4] = {nullptr, nullptr, nullptr, nullptr};  // column-exchange streams, one per owner in flight
     sb_timings tm{};
     bool fine_timing = true;
     int trailing_mode = 0;   // 0: fp64 DMMA (mma.sync), 1: tcgen05 int8 Ozaki slices (ozaki.cu)
@@ -755,7 +756,27 @@ static int32_t wide_diag_phase(sb_ctx* c, sb_factor* f, int64_t k0, int nq, int 
             ce.a = c->next_event(); ce.b = c->next_event();
             SB_CUDA(cudaEventRecord(ce.a, st));
         }
-        for (int q = 0; q < nq; q++) SB_TRY(p2p_exchange_col(c, f, *R, k0 + q, st));
+        // The columns of a step come from different owners: their pulls run side by side, one stream per owner
+        // (two columns of the same owner stay in order on one stream, which keeps its counters monotone).
+        static const bool serial = getenv("SB_P2P_SERIAL") != nullptr;
+        if (serial) {
+            for (int q = 0; q < nq; q++) SB_TRY(p2p_exchange_col(c, f, *R, k0 + q, st));
+        } else {
+            cudaEvent_t e0 = c->next_event();
+            SB_CUDA(cudaEventRecord(e0, st));
+            bool used[4] = {false, false, false, false};
+            for (int q = 0; q < nq; q++) {
+                const int xi = (int)((k0 + q) % world) % 4;
+                if (!used[xi]) { SB_CUDA(cudaStreamWaitEvent(c->xstream[xi], e0, 0)); used[xi] = true; }
+                SB_TRY(p2p_exchange_col(c, f, *R, k0 + q, c->xstream[xi]));
+            }
+            for (int xi = 0; xi < 4; xi++) {
+                if (!used[xi]) continue;
+                cudaEvent_t e1 = c->next_event();
+                SB_CUDA(cudaEventRecord(e1, c->xstream[xi]));
+                SB_CUDA(cudaStreamWaitEvent(st, e1, 0));
+            }
+        }
         if (ce.a) { SB_CUDA(cudaEventRecord(ce.b, st)); comm_ev->push_back(ce); }
     }
     double* Din = f->wide_D;
@@ -984,7 +1005,7 @@ static int32_t cholesky_wide(sb_ctx* c, sb_factor* f, int world, int rank) {
     static const int r_env = getenv("SB_LOOKAHEAD_SMS") ? atoi(getenv("SB_LOOKAHEAD_SMS")) : 0;
     static const int p1_env = getenv("SB_WIDE_P1_US") ? atoi(getenv("SB_WIDE_P1_US")) : 0;
     const int reserve_p1 = r_env > 0 ? r_env : LOOKAHEAD_SMS;
-    const double chain_us = p1_env > 0 ? (double)p1_env : (world > 1 ? 1500.0 : 1000.0);
+    const double chain_us = p1_env > 0 ? (double)p1_env : (world > 1 ? 2500.0 : 1200.0);
     const int64_t p1_tiles = (int64_t)(chain_us / 14.5 * (c->num_sms - reserve_p1));   // half-tiles T^B part 1 should last
 
     auto bulk = [&](int64_t s) -> int32_t {      // panel solve + digit planes of step s, trailing stream
@@ -1276,6 +1297,7 @@ int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
         int prio_lo = 0, prio_hi = 0;
         SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         SB_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < 4; i++) SB_CUDA(cudaStreamCreateWithPriority(&c->xstream[i], cudaStreamNonBlocking, prio_hi));
     }
     const char* ft = getenv("SB_FINE_TIMING");
     if (ft && ft[0] == '0') c->fine_timing = false;
@@ -1337,6 +1359,7 @@ int32_t sb_ctx_destroy(sb_ctx* c) {
     for (auto e : c->marks) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (int i = 0; i < 4; i++) if (c->xstream[i]) cudaStreamDestroy(c->xstream[i]);
     delete c;
     return SB_OK;
 }
