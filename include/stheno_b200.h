@@ -16,7 +16,9 @@
  *     SB_ERR_UNSUPPORTED in this round).
  *   - Data pointers may be HOST or DEVICE pointers (classified with
  *     cudaPointerGetAttributes): host buffers are staged through pinned memory inside the
- *     call; device buffers are used in place.  Outputs likewise.
+ *     call; device buffers are used in place.  Outputs likewise.  The library works on its
+ *     own non-blocking streams: a DEVICE buffer must be complete (its producer stream
+ *     synchronised, e.g. CUDA.synchronize() / torch.cuda.synchronize()) before the call.
  *   - The caller owns every buffer it passes for the duration of the call (Julia:
  *     GC.@preserve).  The library owns device memory and the opaque handles; handles are
  *     released with the matching *_destroy (Julia: finalizer).

@@ -1285,7 +1285,7 @@ int32_t sb_ctx_create(int32_t device, sb_ctx** out) {
     SB_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     SB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
+    if (prop.major != 10 || prop.minor != 0) {   // the cubin is sm_100a only (sm_103 would fail at the first launch)
         sb::set_error("libstheno_b200 is built for sm_100a (B200) only; found sm_" +
                       std::to_string(prop.major) + std::to_string(prop.minor));
         return SB_ERR_UNSUPPORTED;
