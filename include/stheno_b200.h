@@ -121,18 +121,18 @@ typedef struct {
 
 typedef struct {
     double assemble_ms; /* K1 tile assembly */
-    double panel_ms;    /* diag-block potrf + panel TRSM */
-    double trailing_ms; /* SYRK/GEMM trailing updates (DMMA) */
+    double panel_ms;    /* panel work on the critical path: first serial phase + the tensor-core panel solves */
+    double trailing_ms; /* SYRK/GEMM trailing updates (tcgen05 int8 slices, or DMMA) */
     double solve_ms;    /* vector triangular solves + reductions */
     double predict_ms;  /* cross assembly + matrix TRSM + mean/var */
-    double comm_ms;     /* NCCL panel broadcast (multi-GPU) */
+    double comm_ms;     /* block-column exchange (peer copies; NCCL broadcast on the fallback path), incl. waiting for the owners */
     double total_ms;
     double trailing_flops; /* algorithmic flops executed by the trailing-update kernel */
     double trailing_kernel_ms; /* sum of per-launch CUDA-event durations of that kernel */
     int64_t trailing_launches;
     int64_t kernel_launches; /* all kernels launched by this library since last reset */
     double trailing_int8_ops; /* int8 tensor-core ops (2 * MACs) issued by the tcgen05 trailing kernel; 0 on the DMMA path */
-    double panel_chain_ms;    /* total duration of the look-ahead panel phases on the second stream (mostly hidden) */
+    double panel_chain_ms;    /* total duration of the serial panel phases on the second stream (hidden under T^B) */
 } sb_timings;
 
 typedef struct sb_ctx sb_ctx;
